@@ -1,0 +1,53 @@
+"""Build `librfest_b200.so` in-tree with nvcc for sm_100a (no other target).
+
+    python -m rfest_b200.build
+
+nvcc cross-compiles without a GPU.  The shared object is git-ignored but travels
+to the GPU box with the repository snapshot.
+"""
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(PKG_DIR, "csrc", "rfb_api.cu")
+LIB = os.path.join(PKG_DIR, "librfest_b200.so")
+HEADERS = [os.path.join(PKG_DIR, "csrc", h) for h in
+           ("common.cuh", "sweep.cuh", "update.cuh", "project.cuh")] + \
+          [os.path.join(os.path.dirname(PKG_DIR), "include", "rfest_b200.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in [SRC] + HEADERS if os.path.exists(p))
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build librfest_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC, "-ldl"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,55 @@
+// Shared definitions of the rfest_b200 CUDA engine (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/rfest_b200.h"
+
+namespace rfb {
+
+constexpr int kMaxSlots = 8;    // design blocks bound to one data set
+constexpr int kMaxHeads = 5;    // dot products per row (merged 'none' filters count once)
+constexpr int kNumScalars = 16; // per-sweep scalar sums (8 fixed + one per head, padded)
+constexpr int kNlAbsent = 100;  // internal nonlinearity code: head without data, contributes 0
+
+// layout of the scalar part of a sweep's accumulator vector
+enum ScalarSlot {
+  S_LOSS_A = 0,  // poisson: sum(-log(r') * y)   gaussian: sum((y - r)^2)
+  S_LOSS_B = 1,  // poisson: sum(r')
+  S_R = 2,       // sum r
+  S_RR = 3,      // sum r^2
+  S_YR = 4,      // sum y r
+  S_SQERR = 5,   // sum (y - r)^2
+  S_GGLOBAL = 6, // d loss / d intercept['global'] = sum delta
+  S_BAD = 7,     // rows whose prediction is NaN
+  S_GHEAD = 8    // + h: d loss / d (head intercept) = sum delta * phi_h'(a_h)
+};
+
+struct SweepArgs {
+  const float* slot_ptr[kMaxSlots]; // block base pointers (row-major)
+  long long slot_ld[kMaxSlots];     // row strides in floats (multiples of 4)
+  int slot_chunk0[kMaxSlots + 1];   // prefix sums of float4 chunks per slot
+  int n_slots;
+  int n_chunks;                     // total float4 chunks per row = Ctot / 4
+  long long n_rows;
+  const float* y;                   // [n_rows] or nullptr (prediction only)
+  const float* W;                   // [H][Ctot] dense head weights
+  const float* head_icpt;           // [H]
+  const float* glob_icpt;           // [1]
+  int head_nl[kMaxHeads];
+  int out_nl;
+  int distr;
+  float two_over_n;                 // gaussian: 2 / n_global
+  double* warp_acc;                 // [total warps][NE] scratch (L2 resident)
+  double* cta_part;                 // [grid][NE] per-CTA partial sums (output)
+  float* r_out;                     // optional [n_rows]
+  int flush_tiles;                  // fp32 -> fp64 flush cadence, in tiles
+};
+
+__host__ __device__ inline int sweep_num_entries(int H, int n_chunks) {
+  return H * n_chunks * 4 + kNumScalars;
+}
+
+}  // namespace rfb

@@ -1,0 +1,161 @@
+// K1: fused time-lag + spline projection, never materialising the lagged (Hankel) design.
+//
+// Replaces build_design_matrix(...)[burn_in:] @ build_spline_matrix(...)
+// (rfest/utils.py:5-67, rfest/splines.py:278-305, rfest/GLM/_glm.py:250-258,297-298).
+// Because S = kron(St, Sxy), the product separates:
+//   K1a  Z[s, q]            = sum_p stim[s, p] * Sxy[p, q]            (spatial contraction)
+//   K1b  XS[t, a*n_q + q]   = sum_i Z[t + i - front, q] * St[i, a]    (temporal, Hankel)
+// The integer lag/shift/padding map (which raw row feeds design row t, lag i) is exactly the
+// reference's: src = t + i - front, front = nlag + shift - 1 (0 when nlag + shift <= 0), zero
+// outside [0, n_raw_total).
+#pragma once
+
+#include "common.cuh"
+
+namespace rfb {
+
+// ---- K1a: Z = stim @ Sxy, fp32 FMA, shared-memory tiled ------------------------------------------
+// Block tile: 64 rows x 128 columns of Z; K tile 32.  Thread (ty, tx), 16 x 32 threads:
+// rows ty*4..ty*4+3, columns tx + 32*j (j < 4).
+constexpr int kSpTM = 64, kSpTN = 128, kSpTK = 32;
+__global__ void __launch_bounds__(512)
+spatial_project_kernel(const float* __restrict__ stim, long long n_rows, int n_pix,
+                       const float* __restrict__ Sxy, int n_q, float* __restrict__ Z, int ldz) {
+  __shared__ float As[kSpTM][kSpTK + 1];
+  __shared__ float Bs[kSpTK][kSpTN];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long row0 = (long long)blockIdx.x * kSpTM;
+  const int q0 = blockIdx.y * kSpTN;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+
+  for (int k0 = 0; k0 < n_pix; k0 += kSpTK) {
+    // stim tile: 64 x 32, thread loads 4 elements, coalesced along k
+    for (int e = threadIdx.x; e < kSpTM * kSpTK; e += blockDim.x) {
+      const int r = e / kSpTK, k = e % kSpTK;
+      const long long row = row0 + r;
+      As[r][k] = (row < n_rows && k0 + k < n_pix) ? stim[row * n_pix + k0 + k] : 0.f;
+    }
+    for (int e = threadIdx.x; e < kSpTK * kSpTN; e += blockDim.x) {
+      const int k = e / kSpTN, q = e % kSpTN;
+      Bs[k][q] = (k0 + k < n_pix && q0 + q < n_q) ? Sxy[(size_t)(k0 + k) * n_q + q0 + q] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kSpTK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) av[r] = As[ty * 4 + r][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx + 32 * j];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = fmaf(av[r], bv[j], acc[r][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long row = row0 + ty * 4 + r;
+    if (row >= n_rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = q0 + tx + 32 * j;
+      if (q < n_q) Z[row * ldz + q] = acc[r][j];
+    }
+  }
+}
+
+// ---- K1b: temporal Hankel contraction ---------------------------------------------------------------
+// Work item = (group of TT consecutive design rows, one q).  Z rows are addressed relative to
+// z_row0 (the raw row held in Z's first row); raw rows outside [0, n_raw_total) contribute zero.
+struct TemporalArgs {
+  const float* Z;        // [n_z x ldz]
+  long long z_src0;      // raw row index of Z row 0
+  long long n_z;
+  int ldz;
+  long long n_raw_total;
+  float* out;            // block storage
+  long long out_ld;
+  long long out_row0;    // first block row to write
+  long long n_out;
+  int col0;
+  long long first_t;     // design row (untrimmed) of block row out_row0
+  long long front;       // zero rows in front (nlag + shift - 1 or 0)
+  int nlag;
+  int df_t;
+  int n_q;
+  const float* St;       // [nlag x DFT] padded with zero columns, device
+};
+
+template <int DFT, int TT>
+__global__ void __launch_bounds__(128) temporal_project_kernel(const TemporalArgs a) {
+  const long long n_groups = (a.n_out + TT - 1) / TT;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_groups * a.n_q) return;
+  const long long grp = item / a.n_q;
+  const int q = (int)(item - grp * a.n_q);
+  const long long k0 = grp * TT;               // first row (relative to out_row0) of this group
+
+  float acc[TT][DFT];
+#pragma unroll
+  for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+    for (int d = 0; d < DFT; ++d) acc[tt][d] = 0.f;
+
+  for (int i = 0; i < a.nlag; ++i) {
+    float st[DFT];
+#pragma unroll
+    for (int d = 0; d < DFT; ++d) st[d] = __ldg(a.St + i * DFT + d);
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) {
+      const long long src = a.first_t + k0 + tt + i - a.front;     // raw row feeding (t, lag i)
+      float z = 0.f;
+      if (src >= 0 && src < a.n_raw_total) {
+        const long long zr = src - a.z_src0;
+        if (zr >= 0 && zr < a.n_z) z = __ldg(a.Z + zr * a.ldz + q);
+      }
+#pragma unroll
+      for (int d = 0; d < DFT; ++d) acc[tt][d] = fmaf(z, st[d], acc[tt][d]);
+    }
+  }
+#pragma unroll
+  for (int tt = 0; tt < TT; ++tt) {
+    const long long k = k0 + tt;
+    if (k >= a.n_out) break;
+    float* dst = a.out + (a.out_row0 + k) * a.out_ld + a.col0 + q;
+#pragma unroll
+    for (int d = 0; d < DFT; ++d)
+      if (d < a.df_t) dst[(size_t)d * a.n_q] = acc[tt][d];
+  }
+}
+
+// sum y, sum y^2 in fp64 (constants of the metrics, rfest/metrics.py:8-12)
+__global__ void __launch_bounds__(256) y_moments_kernel(const float* y, long long n, double* out2) {
+  __shared__ double s0[8], s1[8];
+  double a = 0.0, b = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = (double)y[i];
+    a += v;
+    b += v * v;
+  }
+  for (int m = 16; m >= 1; m >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, m);
+    b += __shfl_xor_sync(0xffffffffu, b, m);
+  }
+  if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = a; s1[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int k = 0; k < 8; ++k) { ta += s0[k]; tb += s1[k]; }
+    out2[2 * blockIdx.x] = ta;
+    out2[2 * blockIdx.x + 1] = tb;
+  }
+}
+
+}  // namespace rfb

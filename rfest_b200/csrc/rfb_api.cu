@@ -1,0 +1,1343 @@
+// C ABI of the rfest_b200 engine (see include/rfest_b200.h).
+//
+// Host-side runtime: engine (device / stream / NCCL), design blocks, model plan (filters ->
+// heads), data sets, the CUDA-graph fit loop.  The kernels live in sweep.cuh (K2/K4),
+// update.cuh (K3) and project.cuh (K1).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "project.cuh"
+#include "sweep.cuh"
+#include "update.cuh"
+
+using namespace rfb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(RFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),       \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+#define TRY(call)              \
+  do {                         \
+    int rc_ = (call);          \
+    if (rc_ != RFB_OK) return rc_; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded at run time (the copy torch already mapped, or the system one)
+// ------------------------------------------------------------------------------------------------
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+static int nccl_load() {
+  if (g_nccl.lib) return RFB_OK;
+  const char* names[] = {getenv("RFB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    if (n && *n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  }
+  if (!lib) return fail(RFB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  NcclApi a;
+  a.lib = lib;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(lib, "ncclAllReduce");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString)
+    return fail(RFB_ERR_NCCL, "libnccl is missing a required symbol");
+  g_nccl = a;
+  return RFB_OK;
+}
+
+#define NC(call)                                                                              \
+  do {                                                                                        \
+    int r_ = (call);                                                                          \
+    if (r_ != 0)                                                                              \
+      return fail(RFB_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_));           \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+struct Scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct rfb_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  int64_t launches = 0;
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  Scratch stage, zbuf, stbuf, sxybuf, small;
+};
+
+static int scratch_reserve(rfb_engine* e, Scratch& s, size_t bytes) {
+  if (s.bytes >= bytes) return RFB_OK;
+  if (s.p) {
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaFree(s.p));
+    s.p = nullptr;
+    s.bytes = 0;
+  }
+  CU(cudaMalloc(&s.p, bytes));
+  s.bytes = bytes;
+  return RFB_OK;
+}
+
+static int use_device(const rfb_engine* e) {
+  CU(cudaSetDevice(e->device));
+  return RFB_OK;
+}
+
+struct rfb_block {
+  rfb_engine* e = nullptr;
+  float* d = nullptr;
+  int64_t n_rows = 0;
+  int n_cols = 0;
+  int64_t ld = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+struct Filter {
+  int slot, nl, n_coef;
+};
+
+struct DataSet {
+  bool bound = false;
+  int n_slots = 0;
+  rfb_block* blocks[kMaxSlots] = {};
+  float* y = nullptr;      // device copy, owned
+  bool has_y = false;
+  int64_t n = 0;
+  double n_total = 0, sy = 0, syy = 0;
+  float* r_buf = nullptr;  // predictions of the last forward pass that asked for them
+};
+
+
+struct SweepBuffers {
+  double* warp_acc = nullptr;
+  double* cta_part = nullptr;
+  size_t warp_acc_bytes = 0, cta_part_bytes = 0;
+  int grid = 0;
+};
+
+struct Plan {
+  bool ok = false;
+  int F = 0, P = 0;
+  int H = 0;   // heads in use
+  int Ht = 0;  // template head count (>= H)
+  int NCH = 0; // template chunks per lane
+  int RB = 0;
+  int n_slots = 0;
+  int slot_chunk0[kMaxSlots + 1] = {};
+  int n_chunks = 0, ctot = 0, NE = 0;
+  std::vector<int> head_of;    // [F]
+  std::vector<int> head_nl;    // [Ht]
+  std::vector<int> entry_of;   // [P]
+  std::vector<int> coef0;      // [F] offset of the filter's coefficients in b
+};
+
+struct ParamSet {  // device-side parameter image + what the sweep reads
+  float* theta = nullptr;
+  double* ic = nullptr;
+  float* W = nullptr;
+  float* head_icpt = nullptr;
+  float* glob_icpt = nullptr;
+  int* entry_of = nullptr;
+  int* head_of = nullptr;
+};
+
+struct Fit {
+  bool active = false;
+  int max_iters = 0, executed = 0, metric = 0;
+  bool has_dev = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int kernels_per_iter = 0;
+  double* step = nullptr;
+  double *cost_train = nullptr, *cost_dev = nullptr, *metric_train = nullptr, *metric_dev = nullptr;
+  float* ring_b = nullptr;
+  double* ring_ic = nullptr;
+  int* it = nullptr;
+  float *m = nullptr, *v = nullptr;
+  double *mi = nullptr, *vi = nullptr;
+  double* fin = nullptr;  // [NE + kNumScalars]: train entries, then dev scalars
+  UpdateArgs ua{};
+  bool finished = false;
+};
+
+struct rfb_model {
+  rfb_engine* e = nullptr;
+  int distr = 0, out_nl = 0;
+  std::vector<Filter> filters;
+  int slot_cols[kMaxSlots] = {};  // padded widths (ld) once known, 0 = unknown
+  DataSet data[3];
+  Plan plan;
+  ParamSet cur, tmp;  // current parameters; scratch image for rfb_model_eval
+  std::vector<float> host_b;
+  std::vector<double> host_ic;
+  bool have_params = false;
+  SweepBuffers sb[3];
+  double* fin_eval = nullptr;
+  Fit fit;
+};
+
+// ------------------------------------------------------------------------------------------------
+// sweep dispatch
+// ------------------------------------------------------------------------------------------------
+typedef void (*SweepFn)(const SweepArgs);
+
+template <int H, int NCH, int RB>
+static SweepFn pick_bwd(bool bwd) {
+  return bwd ? (SweepFn)sweep_kernel<H, NCH, RB, true> : (SweepFn)sweep_kernel<H, NCH, RB, false>;
+}
+
+static int template_heads(int H) { return H <= 1 ? 1 : H <= 2 ? 2 : H <= 3 ? 3 : 5; }
+static int template_chunks(int nch) { return nch <= 1 ? 1 : nch <= 3 ? 3 : nch <= 5 ? 5 : 10; }
+
+// rows per tile for each (heads, chunks-per-lane) instance: bounded by registers
+static SweepFn sweep_instance(int Ht, int NCH, bool bwd, int* RB) {
+#define INST(h, c, rb)                \
+  if (Ht == h && NCH == c) {          \
+    *RB = rb;                         \
+    return pick_bwd<h, c, rb>(bwd);   \
+  }
+  INST(1, 1, 8) INST(1, 3, 8) INST(1, 5, 4) INST(1, 10, 2)
+  INST(2, 1, 8) INST(2, 3, 8) INST(2, 5, 4) INST(2, 10, 1)
+  INST(3, 1, 8) INST(3, 3, 4) INST(3, 5, 2)
+  INST(5, 1, 8) INST(5, 3, 4)
+#undef INST
+  return nullptr;
+}
+
+static int build_plan(rfb_model* m) {
+  Plan& p = m->plan;
+  p = Plan();
+  p.F = (int)m->filters.size();
+  if (p.F == 0) return fail(RFB_ERR_STATE, "model has no filters");
+  if (p.F + 1 > kUpdateThreads) return fail(RFB_ERR_UNSUPPORTED, "too many filters (%d)", p.F);
+  int n_slots = 0;
+  for (auto& f : m->filters) n_slots = std::max(n_slots, f.slot + 1);
+  p.n_slots = n_slots;
+  for (int s = 0; s < n_slots; ++s) {
+    if (m->slot_cols[s] == 0)
+      return fail(RFB_ERR_STATE, "slot %d has no design block bound in any data set", s);
+    p.slot_chunk0[s + 1] = p.slot_chunk0[s] + m->slot_cols[s] / 4;
+  }
+  p.n_chunks = p.slot_chunk0[n_slots];
+  p.ctot = p.n_chunks * 4;
+
+  // heads: every filter with a nonlinearity is its own dot product; 'none' filters on
+  // different slots add up linearly and share one (their intercepts add, too).
+  struct Head { int nl; unsigned slots; };
+  std::vector<Head> heads;
+  p.head_of.resize(p.F);
+  for (int f = 0; f < p.F; ++f) {
+    const Filter& fl = m->filters[f];
+    int h = -1;
+    if (fl.nl == RFB_NL_NONE) {
+      for (int k = 0; k < (int)heads.size(); ++k)
+        if (heads[k].nl == RFB_NL_NONE && !(heads[k].slots & (1u << fl.slot))) { h = k; break; }
+    }
+    if (h < 0) {
+      heads.push_back({fl.nl, 0u});
+      h = (int)heads.size() - 1;
+    }
+    heads[h].slots |= 1u << fl.slot;
+    p.head_of[f] = h;
+  }
+  p.H = (int)heads.size();
+  if (p.H > kMaxHeads)
+    return fail(RFB_ERR_UNSUPPORTED, "%d dot products per sample (max %d)", p.H, kMaxHeads);
+  p.Ht = template_heads(p.H);
+  const int nch = (p.n_chunks + 31) / 32;
+  if (nch > 10)
+    return fail(RFB_ERR_UNSUPPORTED, "%d design columns per sample (max 1280)", p.ctot);
+  p.NCH = template_chunks(nch);
+  if (!sweep_instance(p.Ht, p.NCH, true, &p.RB)) {
+    // fall back to a larger head template that exists for this width
+    return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel for %d heads x %d columns", p.H, p.ctot);
+  }
+  p.head_nl.assign(p.Ht, RFB_NL_NONE);
+  for (int h = 0; h < p.H; ++h) p.head_nl[h] = heads[h].nl;
+  p.NE = sweep_num_entries(p.Ht, p.n_chunks);
+
+  p.coef0.resize(p.F);
+  p.P = 0;
+  for (int f = 0; f < p.F; ++f) {
+    p.coef0[f] = p.P;
+    p.P += m->filters[f].n_coef;
+  }
+  p.entry_of.resize(p.P);
+  for (int f = 0; f < p.F; ++f) {
+    const Filter& fl = m->filters[f];
+    if (fl.n_coef > m->slot_cols[fl.slot])
+      return fail(RFB_ERR_INVALID, "filter %d has %d coefficients but its block has %d columns", f,
+                  fl.n_coef, m->slot_cols[fl.slot]);
+    for (int j = 0; j < fl.n_coef; ++j)
+      p.entry_of[p.coef0[f] + j] = p.head_of[f] * p.ctot + 4 * p.slot_chunk0[fl.slot] + j;
+  }
+  p.ok = true;
+  return RFB_OK;
+}
+
+static int alloc_paramset(rfb_model* m, ParamSet& ps) {
+  const Plan& p = m->plan;
+  CU(cudaMalloc(&ps.theta, sizeof(float) * std::max(p.P, 1)));
+  CU(cudaMalloc(&ps.ic, sizeof(double) * (p.F + 1)));
+  CU(cudaMalloc(&ps.W, sizeof(float) * ((size_t)p.Ht * p.ctot + 4)));
+  CU(cudaMalloc(&ps.head_icpt, sizeof(float) * p.Ht));
+  CU(cudaMalloc(&ps.glob_icpt, sizeof(float)));
+  CU(cudaMalloc(&ps.entry_of, sizeof(int) * std::max(p.P, 1)));
+  CU(cudaMalloc(&ps.head_of, sizeof(int) * p.F));
+  CU(cudaMemsetAsync(ps.W, 0, sizeof(float) * ((size_t)p.Ht * p.ctot + 4), m->e->stream));
+  CU(cudaMemsetAsync(ps.head_icpt, 0, sizeof(float) * p.Ht, m->e->stream));
+  CU(cudaMemcpyAsync(ps.entry_of, p.entry_of.data(), sizeof(int) * p.P, cudaMemcpyHostToDevice,
+                     m->e->stream));
+  CU(cudaMemcpyAsync(ps.head_of, p.head_of.data(), sizeof(int) * p.F, cudaMemcpyHostToDevice,
+                     m->e->stream));
+  CU(cudaStreamSynchronize(m->e->stream));
+  return RFB_OK;
+}
+
+static void free_paramset(ParamSet& ps) {
+  cudaFree(ps.theta); cudaFree(ps.ic); cudaFree(ps.W); cudaFree(ps.head_icpt);
+  cudaFree(ps.glob_icpt); cudaFree(ps.entry_of); cudaFree(ps.head_of);
+  ps = ParamSet();
+}
+
+static UpdateArgs publish_args(const rfb_model* m, const ParamSet& ps) {
+  UpdateArgs a{};
+  a.P = m->plan.P;
+  a.F = m->plan.F;
+  a.H = m->plan.Ht;
+  a.ctot = m->plan.ctot;
+  a.entry_of = ps.entry_of;
+  a.head_of = ps.head_of;
+  a.theta = ps.theta;
+  a.ic = ps.ic;
+  a.W = ps.W;
+  a.head_icpt = ps.head_icpt;
+  a.glob_icpt = ps.glob_icpt;
+  return a;
+}
+
+static int fit_release(rfb_model* m);
+
+static int ensure_plan(rfb_model* m) {
+  if (m->plan.ok) return RFB_OK;
+  TRY(use_device(m->e));
+  TRY(build_plan(m));
+  free_paramset(m->cur);
+  free_paramset(m->tmp);
+  TRY(alloc_paramset(m, m->cur));
+  TRY(alloc_paramset(m, m->tmp));
+  cudaFree(m->fin_eval);
+  CU(cudaMalloc(&m->fin_eval, sizeof(double) * m->plan.NE));
+  if (m->have_params) {
+    if ((int)m->host_b.size() != m->plan.P || (int)m->host_ic.size() != m->plan.F + 1)
+      return fail(RFB_ERR_STATE, "stored parameters do not match the filters");
+    CU(cudaMemcpyAsync(m->cur.theta, m->host_b.data(), sizeof(float) * m->plan.P,
+                       cudaMemcpyHostToDevice, m->e->stream));
+    CU(cudaMemcpyAsync(m->cur.ic, m->host_ic.data(), sizeof(double) * (m->plan.F + 1),
+                       cudaMemcpyHostToDevice, m->e->stream));
+    publish_params_kernel<<<1, kUpdateThreads, 0, m->e->stream>>>(publish_args(m, m->cur));
+    m->e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(m->e->stream));
+  }
+  return RFB_OK;
+}
+
+static void invalidate_plan(rfb_model* m) {
+  m->plan.ok = false;
+}
+
+// Size the launch and allocate the scratch of the sweeps over data set `kind` (not capturable,
+// so it happens before any graph capture).
+static int ensure_sweep_buffers(rfb_model* m, int kind) {
+  const Plan& p = m->plan;
+  DataSet& ds = m->data[kind];
+  rfb_engine* e = m->e;
+  SweepBuffers& sb = m->sb[kind];
+  if (sb.grid != 0) return RFB_OK;
+  int RB = 0;
+  SweepFn fn = sweep_instance(p.Ht, p.NCH, true, &RB);
+  if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSweepThreads, 0));
+  if (occ < 1) occ = 1;
+  const int wpc = kSweepThreads / 32;
+  const int64_t ntiles = (ds.n + RB - 1) / RB;
+  int64_t grid = (int64_t)e->num_sms * occ;
+  const int64_t need = (ntiles + wpc - 1) / wpc;
+  if (grid > need) grid = std::max<int64_t>(need, 1);
+  sb.warp_acc_bytes = sizeof(double) * (size_t)grid * wpc * p.NE;
+  sb.cta_part_bytes = sizeof(double) * (size_t)grid * p.NE;
+  CU(cudaMalloc(&sb.warp_acc, sb.warp_acc_bytes));
+  CU(cudaMalloc(&sb.cta_part, sb.cta_part_bytes));
+  sb.grid = (int)grid;
+  return RFB_OK;
+}
+
+// Launch one sweep over data set `kind` with the parameter image `ps`.  Leaves the per-CTA
+// partial sums in m->sb[kind].cta_part (grid rows).
+static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* head_nl, bool bwd,
+                        float* r_out) {
+  const Plan& p = m->plan;
+  DataSet& ds = m->data[kind];
+  rfb_engine* e = m->e;
+  int RB = 0;
+  SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd, &RB);
+  if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
+  TRY(ensure_sweep_buffers(m, kind));
+  SweepBuffers& sb = m->sb[kind];
+
+  SweepArgs a{};
+  a.n_slots = p.n_slots;
+  for (int s = 0; s < p.n_slots; ++s) {
+    rfb_block* b = s < ds.n_slots ? ds.blocks[s] : nullptr;
+    a.slot_ptr[s] = b ? b->d : nullptr;
+    a.slot_ld[s] = b ? b->ld : 0;
+  }
+  for (int s = 0; s <= p.n_slots; ++s) a.slot_chunk0[s] = p.slot_chunk0[s];
+  a.n_chunks = p.n_chunks;
+  a.n_rows = ds.n;
+  a.y = ds.has_y ? ds.y : nullptr;
+  a.W = ps.W;
+  a.head_icpt = ps.head_icpt;
+  a.glob_icpt = ps.glob_icpt;
+  for (int h = 0; h < kMaxHeads; ++h) a.head_nl[h] = h < p.Ht ? head_nl[h] : RFB_NL_NONE;
+  a.out_nl = m->out_nl;
+  a.distr = m->distr;
+  a.two_over_n = ds.n_total > 0 ? (float)(2.0 / ds.n_total) : 0.f;
+  a.warp_acc = sb.warp_acc;
+  a.cta_part = sb.cta_part;
+  a.r_out = r_out;
+  a.flush_tiles = std::max(1, 256 / RB);
+  fn<<<sb.grid, kSweepThreads, 0, e->stream>>>(a);
+  e->launches++;
+  CU(cudaGetLastError());
+  return RFB_OK;
+}
+
+// Reduce per-CTA partial rows in a fixed order.  Segment 0: entries [e0, e0 + n0) of the
+// partial rows of `kind0` -> out0; optional segment 1 likewise (kind1 < 0: none).
+static int launch_reduce(rfb_model* m, int kind0, int e0, int n0, double* out0, int kind1, int e1,
+                         int n1, double* out1) {
+  const Plan& p = m->plan;
+  ReduceSeg s0{m->sb[kind0].cta_part + e0, m->sb[kind0].grid, p.NE, n0, out0};
+  const int blocks0 = (n0 + kReduceEx - 1) / kReduceEx;
+  ReduceSeg s1{nullptr, 0, 0, 0, nullptr};
+  int blocks1 = 0;
+  if (kind1 >= 0) {
+    s1 = ReduceSeg{m->sb[kind1].cta_part + e1, m->sb[kind1].grid, p.NE, n1, out1};
+    blocks1 = (n1 + kReduceEx - 1) / kReduceEx;
+  }
+  reduce_partials_kernel<<<blocks0 + blocks1, dim3(kReduceEx, kReduceEy), 0, m->e->stream>>>(s0, s1, blocks0);
+  m->e->launches++;
+  CU(cudaGetLastError());
+  return RFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: misc / engine
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* rfb_last_error(void) { return g_err.c_str(); }
+extern "C" int rfb_abi_version(void) { return RFB_ABI_VERSION; }
+
+extern "C" int rfb_engine_create(int device, rfb_engine** out) {
+  if (!out) return fail(RFB_ERR_INVALID, "out is NULL");
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count)
+    return fail(RFB_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(RFB_ERR_UNSUPPORTED, "rfest_b200 is built for sm_100a only; device %d is sm_%d%d",
+                device, prop.major, prop.minor);
+  rfb_engine* e = new rfb_engine();
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  *out = e;
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_destroy(rfb_engine* e) {
+  if (!e) return RFB_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (Scratch* s : {&e->stage, &e->zbuf, &e->stbuf, &e->sxybuf, &e->small}) cudaFree(s->p);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_synchronize(rfb_engine* e) {
+  if (!e) return fail(RFB_ERR_INVALID, "engine is NULL");
+  TRY(use_device(e));
+  CU(cudaStreamSynchronize(e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_launch_count(rfb_engine* e, int64_t* out) {
+  if (!e || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  *out = e->launches;
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_stream(rfb_engine* e, uint64_t* out) {
+  if (!e || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  *out = (uint64_t)(uintptr_t)e->stream;
+  return RFB_OK;
+}
+
+extern "C" int rfb_comm_unique_id(void* out128) {
+  if (!out128) return fail(RFB_ERR_INVALID, "out128 is NULL");
+  TRY(nccl_load());
+  NcclUid id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_comm_init(rfb_engine* e, const void* id128, int rank, int world) {
+  if (!e || !id128) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(RFB_ERR_INVALID, "bad rank/world");
+  if (e->comm) return fail(RFB_ERR_STATE, "communicator already initialised");
+  if (world == 1) {
+    e->rank = 0;
+    e->world = 1;
+    return RFB_OK;
+  }
+  TRY(nccl_load());
+  TRY(use_device(e));
+  NcclUid id;
+  memcpy(&id, id128, sizeof(id));
+  NC(g_nccl.CommInitRank(&e->comm, world, id, rank));
+  e->rank = rank;
+  e->world = world;
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_comm_info(rfb_engine* e, int* rank, int* world) {
+  if (!e) return fail(RFB_ERR_INVALID, "engine is NULL");
+  if (rank) *rank = e->rank;
+  if (world) *world = e->world;
+  return RFB_OK;
+}
+
+static int allreduce_device_f64(rfb_engine* e, double* d, size_t count) {
+  if (!e->comm) return RFB_OK;
+  NC(g_nccl.AllReduce(d, d, count, kNcclFloat64, kNcclSum, e->comm, e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_allreduce_f64(rfb_engine* e, double* host, int count) {
+  if (!e || !host || count < 0) return fail(RFB_ERR_INVALID, "bad argument");
+  if (!e->comm || count == 0) return RFB_OK;
+  TRY(use_device(e));
+  TRY(scratch_reserve(e, e->small, sizeof(double) * count));
+  double* d = (double*)e->small.p;
+  CU(cudaMemcpyAsync(d, host, sizeof(double) * count, cudaMemcpyHostToDevice, e->stream));
+  TRY(allreduce_device_f64(e, d, count));
+  CU(cudaMemcpyAsync(host, d, sizeof(double) * count, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return RFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: blocks and projection
+// ------------------------------------------------------------------------------------------------
+extern "C" int rfb_block_create(rfb_engine* e, int64_t n_rows, int n_cols, rfb_block** out) {
+  if (!e || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (n_rows <= 0 || n_cols <= 0) return fail(RFB_ERR_INVALID, "empty block %lld x %d", (long long)n_rows, n_cols);
+  TRY(use_device(e));
+  rfb_block* b = new rfb_block();
+  b->e = e;
+  b->n_rows = n_rows;
+  b->n_cols = n_cols;
+  b->ld = ((int64_t)n_cols + 3) / 4 * 4;
+  const size_t bytes = sizeof(float) * (size_t)b->ld * (size_t)n_rows;
+  cudaError_t err = cudaMalloc(&b->d, bytes);
+  if (err != cudaSuccess) {
+    delete b;
+    return fail(RFB_ERR_CUDA, "cudaMalloc of a %lld x %d block (%.2f GB) failed: %s",
+                (long long)n_rows, n_cols, bytes / 1e9, cudaGetErrorString(err));
+  }
+  CU(cudaMemsetAsync(b->d, 0, bytes, e->stream));
+  *out = b;
+  return RFB_OK;
+}
+
+extern "C" int rfb_block_destroy(rfb_block* b) {
+  if (!b) return RFB_OK;
+  cudaSetDevice(b->e->device);
+  cudaStreamSynchronize(b->e->stream);
+  cudaFree(b->d);
+  delete b;
+  return RFB_OK;
+}
+
+extern "C" int rfb_block_shape(const rfb_block* b, int64_t* n_rows, int* n_cols, int64_t* ld) {
+  if (!b) return fail(RFB_ERR_INVALID, "block is NULL");
+  if (n_rows) *n_rows = b->n_rows;
+  if (n_cols) *n_cols = b->n_cols;
+  if (ld) *ld = b->ld;
+  return RFB_OK;
+}
+
+extern "C" int rfb_block_device_ptr(const rfb_block* b, uint64_t* out) {
+  if (!b || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  *out = (uint64_t)(uintptr_t)b->d;
+  return RFB_OK;
+}
+
+extern "C" int rfb_block_read(rfb_block* b, int64_t row0, int64_t n, float* host_out) {
+  if (!b || !host_out) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (row0 < 0 || n < 0 || row0 + n > b->n_rows) return fail(RFB_ERR_INVALID, "row range out of bounds");
+  if (n == 0) return RFB_OK;
+  TRY(use_device(b->e));
+  CU(cudaMemcpy2DAsync(host_out, sizeof(float) * b->n_cols, b->d + row0 * b->ld, sizeof(float) * b->ld,
+                       sizeof(float) * b->n_cols, (size_t)n, cudaMemcpyDeviceToHost, b->e->stream));
+  CU(cudaStreamSynchronize(b->e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_block_write(rfb_block* b, int64_t row0, int64_t n, const float* src, int on_device) {
+  if (!b || !src) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (row0 < 0 || n < 0 || row0 + n > b->n_rows) return fail(RFB_ERR_INVALID, "row range out of bounds");
+  if (n == 0) return RFB_OK;
+  TRY(use_device(b->e));
+  CU(cudaMemcpy2DAsync(b->d + row0 * b->ld, sizeof(float) * b->ld, src, sizeof(float) * b->n_cols,
+                       sizeof(float) * b->n_cols, (size_t)n,
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->e->stream));
+  CU(cudaStreamSynchronize(b->e->stream));
+  return RFB_OK;
+}
+
+template <int DFT>
+static void launch_temporal(const TemporalArgs& a, cudaStream_t s) {
+  constexpr int TT = DFT <= 8 ? 8 : 4;
+  const long long groups = (a.n_out + TT - 1) / TT;
+  const long long items = groups * a.n_q;
+  const int threads = 128;
+  const long long blocks = (items + threads - 1) / threads;
+  temporal_project_kernel<DFT, TT><<<(unsigned)blocks, threads, 0, s>>>(a);
+}
+
+extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out, int col0,
+                                 const float* stim, int on_device, int64_t src0, int64_t n_src,
+                                 int64_t n_raw_total, int n_pix, int64_t first_t, int nlag, int shift,
+                                 const float* St, int df_t, const float* Sxy, int n_q) {
+  if (!dst || !stim || !St) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (nlag < 1 || df_t < 1 || n_pix < 1 || n_q < 1) return fail(RFB_ERR_INVALID, "bad dims");
+  if (df_t > 16) return fail(RFB_ERR_UNSUPPORTED, "df of the time axis > 16 (%d)", df_t);
+  if (!Sxy && (n_pix != 1 || n_q != 1)) return fail(RFB_ERR_INVALID, "Sxy is NULL but n_pix/n_q != 1");
+  if (dst_row0 < 0 || n_out < 0 || dst_row0 + n_out > dst->n_rows)
+    return fail(RFB_ERR_INVALID, "destination rows out of bounds");
+  if (col0 < 0 || col0 + df_t * n_q > dst->n_cols) return fail(RFB_ERR_INVALID, "destination columns out of bounds");
+  if (n_src < 0 || src0 < 0 || src0 + n_src > n_raw_total) return fail(RFB_ERR_INVALID, "bad source range");
+  if (n_out == 0) return RFB_OK;
+  rfb_engine* e = dst->e;
+  TRY(use_device(e));
+
+  const int64_t front = (nlag + shift > 0) ? (int64_t)nlag + shift - 1 : 0;   // rfest/utils.py:54-57
+  // every raw row this call needs must have been supplied
+  {
+    int64_t lo = first_t - front, hi = first_t + n_out - 1 + nlag - 1 - front;
+    lo = std::max<int64_t>(lo, 0);
+    hi = std::min<int64_t>(hi, n_raw_total - 1);
+    if (lo <= hi && (lo < src0 || hi >= src0 + n_src))
+      return fail(RFB_ERR_INVALID,
+                  "rows [%lld, %lld] of the input are needed but [%lld, %lld) were supplied (halo missing)",
+                  (long long)lo, (long long)hi, (long long)src0, (long long)(src0 + n_src));
+  }
+
+  const int DFT = df_t <= 1 ? 1 : df_t <= 2 ? 2 : df_t <= 4 ? 4 : df_t <= 8 ? 8 : df_t <= 12 ? 12 : 16;
+  {
+    std::vector<float> stp((size_t)nlag * DFT, 0.f);
+    for (int i = 0; i < nlag; ++i)
+      for (int d = 0; d < df_t; ++d) stp[(size_t)i * DFT + d] = St[(size_t)i * df_t + d];
+    TRY(scratch_reserve(e, e->stbuf, sizeof(float) * stp.size()));
+    CU(cudaMemcpyAsync(e->stbuf.p, stp.data(), sizeof(float) * stp.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  const float* d_sxy = nullptr;
+  if (Sxy) {
+    TRY(scratch_reserve(e, e->sxybuf, sizeof(float) * (size_t)n_pix * n_q));
+    CU(cudaMemcpyAsync(e->sxybuf.p, Sxy, sizeof(float) * (size_t)n_pix * n_q, cudaMemcpyHostToDevice, e->stream));
+    d_sxy = (const float*)e->sxybuf.p;
+  }
+
+  int64_t chunk = (int64_t)(64u << 20) / n_pix;  // ~256 MB of staged stimulus per chunk
+  chunk = std::min<int64_t>(std::max<int64_t>(chunk, 4096), 1 << 20);
+  for (int64_t k0 = 0; k0 < n_out; k0 += chunk) {
+    const int64_t kc = std::min<int64_t>(chunk, n_out - k0);
+    int64_t lo = first_t + k0 - front, hi = first_t + k0 + kc - 1 + nlag - 1 - front;
+    lo = std::max<int64_t>(lo, 0);
+    hi = std::min<int64_t>(hi, n_raw_total - 1);
+    const int64_t nz = hi >= lo ? hi - lo + 1 : 0;
+
+    const float* d_z = nullptr;
+    int ldz = n_q;
+    if (nz > 0) {
+      const float* d_stim = nullptr;
+      if (on_device) {
+        d_stim = stim + (lo - src0) * (int64_t)n_pix;
+      } else {
+        TRY(scratch_reserve(e, e->stage, sizeof(float) * (size_t)nz * n_pix));
+        CU(cudaMemcpyAsync(e->stage.p, stim + (lo - src0) * (int64_t)n_pix, sizeof(float) * (size_t)nz * n_pix,
+                           cudaMemcpyHostToDevice, e->stream));
+        d_stim = (const float*)e->stage.p;
+      }
+      if (Sxy) {
+        TRY(scratch_reserve(e, e->zbuf, sizeof(float) * (size_t)nz * n_q));
+        dim3 grid((unsigned)((nz + kSpTM - 1) / kSpTM), (unsigned)((n_q + kSpTN - 1) / kSpTN));
+        spatial_project_kernel<<<grid, 512, 0, e->stream>>>(d_stim, nz, n_pix, d_sxy, n_q, (float*)e->zbuf.p, n_q);
+        e->launches++;
+        CU(cudaGetLastError());
+        d_z = (const float*)e->zbuf.p;
+      } else {
+        d_z = d_stim;
+        ldz = 1;
+      }
+    }
+    TemporalArgs a{};
+    a.Z = d_z;
+    a.z_src0 = lo;
+    a.n_z = nz;
+    a.ldz = ldz;
+    a.n_raw_total = n_raw_total;
+    a.out = dst->d;
+    a.out_ld = dst->ld;
+    a.out_row0 = dst_row0 + k0;
+    a.n_out = kc;
+    a.col0 = col0;
+    a.first_t = first_t + k0;
+    a.front = front;
+    a.nlag = nlag;
+    a.df_t = df_t;
+    a.n_q = n_q;
+    a.St = (const float*)e->stbuf.p;
+    switch (DFT) {
+      case 1: launch_temporal<1>(a, e->stream); break;
+      case 2: launch_temporal<2>(a, e->stream); break;
+      case 4: launch_temporal<4>(a, e->stream); break;
+      case 8: launch_temporal<8>(a, e->stream); break;
+      case 12: launch_temporal<12>(a, e->stream); break;
+      default: launch_temporal<16>(a, e->stream); break;
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    if (!on_device) CU(cudaStreamSynchronize(e->stream));  // the staging buffer is reused
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return RFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: model
+// ------------------------------------------------------------------------------------------------
+static bool valid_nl(int nl) { return nl >= RFB_NL_NONE && nl <= RFB_NL_LEAKY_RELU; }
+
+extern "C" int rfb_model_create(rfb_engine* e, int distr, int output_nl, rfb_model** out) {
+  if (!e || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (distr != RFB_DISTR_GAUSSIAN && distr != RFB_DISTR_POISSON)
+    return fail(RFB_ERR_UNSUPPORTED, "unknown distribution %d", distr);
+  if (!valid_nl(output_nl)) return fail(RFB_ERR_UNSUPPORTED, "unknown output nonlinearity %d", output_nl);
+  rfb_model* m = new rfb_model();
+  m->e = e;
+  m->distr = distr;
+  m->out_nl = output_nl;
+  *out = m;
+  return RFB_OK;
+}
+
+static void free_sweep_buffers(rfb_model* m) {
+  for (auto& sb : m->sb) {
+    cudaFree(sb.warp_acc);
+    cudaFree(sb.cta_part);
+    sb = SweepBuffers();
+  }
+}
+
+extern "C" int rfb_model_destroy(rfb_model* m) {
+  if (!m) return RFB_OK;
+  cudaSetDevice(m->e->device);
+  cudaStreamSynchronize(m->e->stream);
+  fit_release(m);
+  free_paramset(m->cur);
+  free_paramset(m->tmp);
+  free_sweep_buffers(m);
+  cudaFree(m->fin_eval);
+  for (auto& ds : m->data) {
+    cudaFree(ds.y);
+    cudaFree(ds.r_buf);
+  }
+  delete m;
+  return RFB_OK;
+}
+
+extern "C" int rfb_model_clear_filters(rfb_model* m) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  TRY(use_device(m->e));
+  CU(cudaStreamSynchronize(m->e->stream));
+  fit_release(m);
+  m->filters.clear();
+  m->have_params = false;
+  invalidate_plan(m);
+  free_sweep_buffers(m);
+  return RFB_OK;
+}
+
+extern "C" int rfb_model_add_filter(rfb_model* m, int slot, int filter_nl, int n_coef) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  if (slot < 0 || slot >= kMaxSlots) return fail(RFB_ERR_UNSUPPORTED, "slot %d out of range (max %d)", slot, kMaxSlots);
+  if (!valid_nl(filter_nl)) return fail(RFB_ERR_UNSUPPORTED, "unknown filter nonlinearity %d", filter_nl);
+  if (n_coef < 1) return fail(RFB_ERR_INVALID, "filter needs at least one coefficient");
+  if (m->fit.active) return fail(RFB_ERR_STATE, "cannot add filters during a fit");
+  m->filters.push_back({slot, filter_nl, n_coef});
+  m->have_params = false;
+  invalidate_plan(m);
+  free_sweep_buffers(m);
+  return (int)m->filters.size() - 1;
+}
+
+extern "C" int rfb_model_set_data(rfb_model* m, int kind, int n_slots, rfb_block* const* blocks,
+                                  const float* y, int y_on_device, int64_t n) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  if (n_slots < 1 || n_slots > kMaxSlots || !blocks) return fail(RFB_ERR_INVALID, "bad slots");
+  if (n <= 0) return fail(RFB_ERR_INVALID, "data set is empty");
+  if (m->fit.active) return fail(RFB_ERR_STATE, "cannot rebind data during a fit");
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  for (int s = 0; s < n_slots; ++s) {
+    rfb_block* b = blocks[s];
+    if (!b) continue;  // filter without data in this set (allowed for prediction)
+    if (b->e != e) return fail(RFB_ERR_INVALID, "block %d belongs to another engine", s);
+    if (b->n_rows != n) return fail(RFB_ERR_INVALID, "block %d has %lld rows, expected %lld", s,
+                                    (long long)b->n_rows, (long long)n);
+    if (m->slot_cols[s] != 0 && m->slot_cols[s] != (int)b->ld) {
+      if (kind != RFB_KIND_TRAIN)
+        return fail(RFB_ERR_INVALID, "block %d has %d columns but the slot was registered with %d", s,
+                    (int)b->ld, m->slot_cols[s]);
+      invalidate_plan(m);
+    }
+    if (m->slot_cols[s] != (int)b->ld) {
+      m->slot_cols[s] = (int)b->ld;
+      invalidate_plan(m);
+    }
+  }
+  DataSet& ds = m->data[kind];
+  CU(cudaStreamSynchronize(e->stream));
+  cudaFree(ds.y);
+  cudaFree(ds.r_buf);
+  ds = DataSet();
+  ds.bound = true;
+  ds.n_slots = n_slots;
+  for (int s = 0; s < n_slots; ++s) ds.blocks[s] = blocks[s];
+  ds.n = n;
+  cudaFree(m->sb[kind].warp_acc);
+  cudaFree(m->sb[kind].cta_part);
+  m->sb[kind] = SweepBuffers();
+  double mom[3] = {(double)n, 0.0, 0.0};
+  if (y) {
+    CU(cudaMalloc(&ds.y, sizeof(float) * (size_t)n));
+    CU(cudaMemcpyAsync(ds.y, y, sizeof(float) * (size_t)n,
+                       y_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    ds.has_y = true;
+    const int blocks_y = (int)std::min<int64_t>(512, (n + 255) / 256);
+    TRY(scratch_reserve(e, e->small, sizeof(double) * 2 * 512));
+    y_moments_kernel<<<blocks_y, 256, 0, e->stream>>>(ds.y, n, (double*)e->small.p);
+    e->launches++;
+    CU(cudaGetLastError());
+    std::vector<double> part(2 * blocks_y);
+    CU(cudaMemcpyAsync(part.data(), e->small.p, sizeof(double) * 2 * blocks_y, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < blocks_y; ++k) {
+      mom[1] += part[2 * k];
+      mom[2] += part[2 * k + 1];
+    }
+  }
+  TRY(rfb_engine_allreduce_f64(e, mom, 3));
+  ds.n_total = mom[0];
+  ds.sy = mom[1];
+  ds.syy = mom[2];
+  return RFB_OK;
+}
+
+extern "C" int rfb_model_n_params(rfb_model* m, int* n_coef_total, int* n_intercepts) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  int P = 0;
+  for (auto& f : m->filters) P += f.n_coef;
+  if (n_coef_total) *n_coef_total = P;
+  if (n_intercepts) *n_intercepts = (int)m->filters.size() + 1;
+  return RFB_OK;
+}
+
+extern "C" int rfb_model_set_params(rfb_model* m, const float* b, const double* intercepts) {
+  if (!m || !b || !intercepts) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (m->fit.active) return fail(RFB_ERR_STATE, "cannot set parameters during a fit");
+  int P = 0, K = 0;
+  rfb_model_n_params(m, &P, &K);
+  m->host_b.assign(b, b + P);
+  m->host_ic.assign(intercepts, intercepts + K);
+  m->have_params = true;
+  if (m->plan.ok) {
+    rfb_engine* e = m->e;
+    TRY(use_device(e));
+    CU(cudaMemcpyAsync(m->cur.theta, m->host_b.data(), sizeof(float) * P, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(m->cur.ic, m->host_ic.data(), sizeof(double) * K, cudaMemcpyHostToDevice, e->stream));
+    publish_params_kernel<<<1, kUpdateThreads, 0, e->stream>>>(publish_args(m, m->cur));
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  return RFB_OK;
+}
+
+extern "C" int rfb_model_get_params(rfb_model* m, float* b, double* intercepts) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  if (!m->have_params) return fail(RFB_ERR_STATE, "no parameters set");
+  if (m->plan.ok) {
+    rfb_engine* e = m->e;
+    TRY(use_device(e));
+    CU(cudaMemcpyAsync(m->host_b.data(), m->cur.theta, sizeof(float) * m->plan.P, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(m->host_ic.data(), m->cur.ic, sizeof(double) * (m->plan.F + 1), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  if (b) memcpy(b, m->host_b.data(), sizeof(float) * m->host_b.size());
+  if (intercepts) memcpy(intercepts, m->host_ic.data(), sizeof(double) * m->host_ic.size());
+  return RFB_OK;
+}
+
+extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const double* intercepts,
+                              float* r_out, double* sums) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  DataSet& ds = m->data[kind];
+  if (!ds.bound) return fail(RFB_ERR_STATE, "no data bound for kind %d", kind);
+  if ((b == nullptr) != (intercepts == nullptr)) return fail(RFB_ERR_INVALID, "pass both b and intercepts or neither");
+  if (!b && !m->have_params) return fail(RFB_ERR_STATE, "no parameters set");
+  TRY(ensure_plan(m));
+  rfb_engine* e = m->e;
+  const Plan& p = m->plan;
+  TRY(use_device(e));
+
+  // parameter image for this evaluation; filters without data in this set drop out
+  // (forwardpass only loops over self.X[kind], _glm.py:555)
+  std::vector<float> hb(p.P);
+  std::vector<double> hic(p.F + 1);
+  if (b) {
+    std::copy(b, b + p.P, hb.begin());
+    std::copy(intercepts, intercepts + p.F + 1, hic.begin());
+  } else {
+    TRY(rfb_model_get_params(m, hb.data(), hic.data()));
+  }
+  std::vector<int> head_of(p.head_of), head_nl(p.head_nl);
+  std::vector<char> head_live(p.Ht, 0);
+  for (int f = 0; f < p.F; ++f) {
+    const int s = m->filters[f].slot;
+    const bool present = s < ds.n_slots && ds.blocks[s] != nullptr;
+    if (present) {
+      head_live[p.head_of[f]] = 1;
+    } else {
+      for (int j = 0; j < m->filters[f].n_coef; ++j) hb[p.coef0[f] + j] = 0.f;
+      hic[f] = 0.0;
+    }
+  }
+  for (int h = 0; h < p.H; ++h)
+    if (!head_live[h]) head_nl[h] = kNlAbsent;
+  CU(cudaMemcpyAsync(m->tmp.theta, hb.data(), sizeof(float) * p.P, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(m->tmp.ic, hic.data(), sizeof(double) * (p.F + 1), cudaMemcpyHostToDevice, e->stream));
+  publish_params_kernel<<<1, kUpdateThreads, 0, e->stream>>>(publish_args(m, m->tmp));
+  e->launches++;
+  CU(cudaGetLastError());
+
+  float* d_r = nullptr;
+  if (r_out) {
+    if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * (size_t)ds.n));
+    d_r = ds.r_buf;
+  }
+  TRY(launch_sweep(m, kind, m->tmp, head_nl.data(), false, d_r));
+  // only the scalar tail matters for a forward pass
+  double* d_sc = m->fin_eval;
+  TRY(launch_reduce(m, kind, p.Ht * p.ctot, kNumScalars, d_sc, -1, 0, 0, nullptr));
+  TRY(allreduce_device_f64(e, d_sc, kNumScalars));
+  double sc[kNumScalars];
+  CU(cudaMemcpyAsync(sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, e->stream));
+  if (r_out) CU(cudaMemcpyAsync(r_out, d_r, sizeof(float) * (size_t)ds.n, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (sums) {
+    sums[RFB_SUM_LOSS_A] = sc[S_LOSS_A];
+    sums[RFB_SUM_LOSS_B] = sc[S_LOSS_B];
+    sums[RFB_SUM_R] = sc[S_R];
+    sums[RFB_SUM_RR] = sc[S_RR];
+    sums[RFB_SUM_YR] = sc[S_YR];
+    sums[RFB_SUM_SQERR] = sc[S_SQERR];
+    sums[RFB_SUM_Y] = ds.sy;
+    sums[RFB_SUM_YY] = ds.syy;
+  }
+  return RFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: fit loop
+// ------------------------------------------------------------------------------------------------
+static int fit_release(rfb_model* m) {
+  Fit& f = m->fit;
+  if (f.exec) cudaGraphExecDestroy(f.exec);
+  if (f.graph) cudaGraphDestroy(f.graph);
+  cudaFree(f.step); cudaFree(f.cost_train); cudaFree(f.cost_dev); cudaFree(f.metric_train);
+  cudaFree(f.metric_dev); cudaFree(f.ring_b); cudaFree(f.ring_ic); cudaFree(f.it);
+  cudaFree(f.m); cudaFree(f.v); cudaFree(f.mi); cudaFree(f.vi); cudaFree(f.fin);
+  f = Fit();
+  return RFB_OK;
+}
+
+static int fill_nan(double* d, int n, cudaStream_t s) {
+  std::vector<double> h(n, std::nan(""));
+  CU(cudaMemcpyAsync(d, h.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));
+  return RFB_OK;
+}
+
+
+// One iteration's kernels in stream order: train sweep, dev sweep, fixed-order reduction,
+// all-reduce over ranks, bookkeeping + Adam.  Captured into the graph by rfb_fit_begin and
+// run eagerly (forward-only) by rfb_fit_finish.
+static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, float* r_dev,
+                             cudaEvent_t* ev = nullptr) {
+  Fit& f = m->fit;
+  const Plan& p = m->plan;
+  rfb_engine* e = m->e;
+  if (ev) CU(cudaEventRecord(ev[0], e->stream));
+  TRY(launch_sweep(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only, r_train));
+  if (ev) CU(cudaEventRecord(ev[1], e->stream));
+  if (f.has_dev) TRY(launch_sweep(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false, r_dev));
+  if (ev) CU(cudaEventRecord(ev[2], e->stream));
+  const int tail = p.Ht * p.ctot;
+  if (final_only) {
+    TRY(launch_reduce(m, RFB_KIND_TRAIN, tail, kNumScalars, f.fin + tail,
+                      f.has_dev ? RFB_KIND_DEV : -1, tail, kNumScalars, f.fin + p.NE));
+    TRY(allreduce_device_f64(e, f.fin + tail, 2 * kNumScalars));   // train tail + dev scalars are adjacent
+  } else {
+    TRY(launch_reduce(m, RFB_KIND_TRAIN, 0, p.NE, f.fin, f.has_dev ? RFB_KIND_DEV : -1, tail,
+                      kNumScalars, f.fin + p.NE));
+    TRY(allreduce_device_f64(e, f.fin, (size_t)p.NE + kNumScalars));
+  }
+  if (ev) CU(cudaEventRecord(ev[3], e->stream));
+  UpdateArgs ua = f.ua;
+  ua.final_only = final_only ? 1 : 0;
+  update_kernel<<<1, kUpdateThreads, 0, e->stream>>>(ua);
+  e->launches++;
+  CU(cudaGetLastError());
+  if (ev) CU(cudaEventRecord(ev[4], e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_begin(rfb_model* m, int max_iters, const double* step_sizes, double alpha,
+                             double beta, int metric) {
+  if (!m || !step_sizes) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (max_iters < 1) return fail(RFB_ERR_INVALID, "max_iters must be >= 1");
+  if (metric < RFB_METRIC_NONE || metric > RFB_METRIC_CORRCOEF) return fail(RFB_ERR_INVALID, "bad metric");
+  if (!m->data[RFB_KIND_TRAIN].bound || !m->data[RFB_KIND_TRAIN].has_y)
+    return fail(RFB_ERR_STATE, "no training data / response bound");
+  if (!m->have_params) return fail(RFB_ERR_STATE, "no initial parameters set");
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  CU(cudaStreamSynchronize(e->stream));
+  fit_release(m);
+  TRY(ensure_plan(m));
+  const Plan& p = m->plan;
+  const DataSet& tr = m->data[RFB_KIND_TRAIN];
+  const DataSet& dev = m->data[RFB_KIND_DEV];
+  for (int s = 0; s < p.n_slots; ++s)
+    if (!(s < tr.n_slots && tr.blocks[s])) return fail(RFB_ERR_STATE, "training data has no block for slot %d", s);
+  Fit& f = m->fit;
+  f.max_iters = max_iters;
+  f.metric = metric;
+  f.has_dev = dev.bound && dev.has_y;
+  if (f.has_dev)
+    for (int s = 0; s < p.n_slots; ++s)
+      if (!(s < dev.n_slots && dev.blocks[s])) return fail(RFB_ERR_STATE, "dev data has no block for slot %d", s);
+
+  const size_t nd = (size_t)max_iters;
+  const size_t np = (size_t)std::max(p.P, 1), nk = (size_t)p.F + 1;
+  CU(cudaMalloc(&f.step, sizeof(double) * nd));
+  CU(cudaMalloc(&f.cost_train, sizeof(double) * nd));
+  CU(cudaMalloc(&f.cost_dev, sizeof(double) * nd));
+  CU(cudaMalloc(&f.metric_train, sizeof(double) * nd));
+  CU(cudaMalloc(&f.metric_dev, sizeof(double) * nd));
+  CU(cudaMalloc(&f.ring_b, sizeof(float) * nd * np));
+  CU(cudaMalloc(&f.ring_ic, sizeof(double) * nd * nk));
+  CU(cudaMalloc(&f.it, sizeof(int)));
+  CU(cudaMalloc(&f.m, sizeof(float) * np));
+  CU(cudaMalloc(&f.v, sizeof(float) * np));
+  CU(cudaMalloc(&f.mi, sizeof(double) * nk));
+  CU(cudaMalloc(&f.vi, sizeof(double) * nk));
+  CU(cudaMalloc(&f.fin, sizeof(double) * ((size_t)p.NE + kNumScalars)));
+  CU(cudaMemcpyAsync(f.step, step_sizes, sizeof(double) * nd, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemsetAsync(f.it, 0, sizeof(int), e->stream));
+  CU(cudaMemsetAsync(f.m, 0, sizeof(float) * np, e->stream));
+  CU(cudaMemsetAsync(f.v, 0, sizeof(float) * np, e->stream));
+  CU(cudaMemsetAsync(f.mi, 0, sizeof(double) * nk, e->stream));
+  CU(cudaMemsetAsync(f.vi, 0, sizeof(double) * nk, e->stream));
+  CU(cudaMemsetAsync(f.fin, 0, sizeof(double) * ((size_t)p.NE + kNumScalars), e->stream));
+  TRY(fill_nan(f.cost_train, max_iters, e->stream));
+  TRY(fill_nan(f.cost_dev, max_iters, e->stream));
+  TRY(fill_nan(f.metric_train, max_iters, e->stream));
+  TRY(fill_nan(f.metric_dev, max_iters, e->stream));
+
+  // start from the stored initial parameters
+  CU(cudaMemcpyAsync(m->cur.theta, m->host_b.data(), sizeof(float) * p.P, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(m->cur.ic, m->host_ic.data(), sizeof(double) * nk, cudaMemcpyHostToDevice, e->stream));
+  publish_params_kernel<<<1, kUpdateThreads, 0, e->stream>>>(publish_args(m, m->cur));
+  e->launches++;
+  CU(cudaGetLastError());
+
+  UpdateArgs& ua = f.ua;
+  ua = publish_args(m, m->cur);
+  ua.m = f.m; ua.v = f.v; ua.mi = f.mi; ua.vi = f.vi;
+  ua.fin_train = f.fin;
+  ua.fin_dev = f.has_dev ? f.fin + p.NE : nullptr;
+  ua.n_train = tr.n_total; ua.sy_train = tr.sy; ua.syy_train = tr.syy;
+  ua.n_dev = dev.n_total; ua.sy_dev = dev.sy; ua.syy_dev = dev.syy;
+  ua.distr = m->distr;
+  ua.metric = metric;
+  ua.alpha = (float)alpha;
+  ua.beta = (float)beta;
+  ua.penalise = beta != 0.0 ? 1 : 0;
+  ua.step_sizes = f.step;
+  ua.cost_train = f.cost_train; ua.cost_dev = f.cost_dev;
+  ua.metric_train = f.metric_train; ua.metric_dev = f.metric_dev;
+  ua.ring_b = f.ring_b; ua.ring_ic = f.ring_ic;
+  ua.it = f.it;
+  ua.max_iters = max_iters;
+  ua.final_only = 0;
+
+  // size the sweeps' scratch outside the capture (allocation is not capturable)
+  TRY(ensure_sweep_buffers(m, RFB_KIND_TRAIN));
+  if (f.has_dev) TRY(ensure_sweep_buffers(m, RFB_KIND_DEV));
+  CU(cudaStreamSynchronize(e->stream));
+
+  const int64_t l0 = e->launches;
+  CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_iteration(m, false, nullptr, nullptr);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+  f.kernels_per_iter = (int)(e->launches - l0);
+  e->launches = l0;  // captured, not executed
+  if (rc != RFB_OK || ce != cudaSuccess || !graph) {
+    std::string msg = rc != RFB_OK ? g_err : std::string(cudaGetErrorString(ce));
+    if (graph) cudaGraphDestroy(graph);
+    fit_release(m);
+    return fail(rc != RFB_OK ? rc : RFB_ERR_CUDA, "capturing the fit iteration failed: %s", msg.c_str());
+  }
+  f.graph = graph;
+  CU(cudaGraphInstantiate(&f.exec, f.graph, 0));
+  f.active = true;
+  f.executed = 0;
+  f.finished = false;
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_run(rfb_model* m, int n_iters) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  Fit& f = m->fit;
+  if (!f.active) return fail(RFB_ERR_STATE, "rfb_fit_begin has not been called");
+  if (f.finished) return fail(RFB_ERR_STATE, "the fit was finished; begin a new one");
+  if (n_iters < 0 || f.executed + n_iters > f.max_iters)
+    return fail(RFB_ERR_INVALID, "%d more iterations exceed max_iters=%d (executed %d)", n_iters, f.max_iters, f.executed);
+  TRY(use_device(m->e));
+  for (int k = 0; k < n_iters; ++k) {
+    CU(cudaGraphLaunch(f.exec, m->e->stream));
+    m->e->launches += f.kernels_per_iter;
+  }
+  f.executed += n_iters;
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_run_timed(rfb_model* m, int n_iters, double* ms4) {
+  if (!m || !ms4) return fail(RFB_ERR_INVALID, "NULL argument");
+  Fit& f = m->fit;
+  if (!f.active) return fail(RFB_ERR_STATE, "rfb_fit_begin has not been called");
+  if (f.finished) return fail(RFB_ERR_STATE, "the fit was finished; begin a new one");
+  if (n_iters < 1 || f.executed + n_iters > f.max_iters)
+    return fail(RFB_ERR_INVALID, "%d more iterations exceed max_iters=%d (executed %d)", n_iters, f.max_iters, f.executed);
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  std::vector<cudaEvent_t> ev((size_t)n_iters * 5);
+  for (auto& x : ev) CU(cudaEventCreate(&x));
+  int rc = RFB_OK;
+  for (int k = 0; k < n_iters && rc == RFB_OK; ++k) rc = enqueue_iteration(m, false, nullptr, nullptr, &ev[(size_t)k * 5]);
+  cudaStreamSynchronize(e->stream);
+  for (int j = 0; j < 4; ++j) ms4[j] = 0.0;
+  if (rc == RFB_OK) {
+    for (int k = 0; k < n_iters; ++k)
+      for (int j = 0; j < 4; ++j) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[(size_t)k * 5 + j], ev[(size_t)k * 5 + j + 1]);
+        ms4[j] += (double)t / n_iters;
+      }
+    f.executed += n_iters;
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return rc;
+}
+
+extern "C" int rfb_fit_iterations(rfb_model* m, int* out) {
+  if (!m || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  *out = m->fit.executed;
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_finish(rfb_model* m, int i_last) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  Fit& f = m->fit;
+  if (!f.active) return fail(RFB_ERR_STATE, "rfb_fit_begin has not been called");
+  if (i_last < 0 || i_last >= f.executed) return fail(RFB_ERR_INVALID, "iteration %d was not executed (%d were)", i_last, f.executed);
+  rfb_engine* e = m->e;
+  const Plan& p = m->plan;
+  TRY(use_device(e));
+  // parameters after update i_last become current
+  CU(cudaMemcpyAsync(m->cur.theta, f.ring_b + (size_t)i_last * std::max(p.P, 1), sizeof(float) * p.P,
+                     cudaMemcpyDeviceToDevice, e->stream));
+  CU(cudaMemcpyAsync(m->cur.ic, f.ring_ic + (size_t)i_last * (p.F + 1), sizeof(double) * (p.F + 1),
+                     cudaMemcpyDeviceToDevice, e->stream));
+  publish_params_kernel<<<1, kUpdateThreads, 0, e->stream>>>(publish_args(m, m->cur));
+  e->launches++;
+  CU(cudaGetLastError());
+  const int it = i_last + 1;
+  CU(cudaMemcpyAsync(f.it, &it, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  DataSet& tr = m->data[RFB_KIND_TRAIN];
+  DataSet& dev = m->data[RFB_KIND_DEV];
+  if (!tr.r_buf) CU(cudaMalloc(&tr.r_buf, sizeof(float) * (size_t)tr.n));
+  if (f.has_dev && !dev.r_buf) CU(cudaMalloc(&dev.r_buf, sizeof(float) * (size_t)dev.n));
+  TRY(enqueue_iteration(m, true, tr.r_buf, f.has_dev ? dev.r_buf : nullptr));
+  CU(cudaStreamSynchronize(e->stream));
+  f.finished = true;
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_traces(rfb_model* m, int n, double* cost_train, double* cost_dev,
+                              double* metric_train, double* metric_dev) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  Fit& f = m->fit;
+  if (!f.active) return fail(RFB_ERR_STATE, "no fit in progress");
+  if (n < 0 || n > f.executed) return fail(RFB_ERR_INVALID, "asked for %d iterations, %d executed", n, f.executed);
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  const size_t bytes = sizeof(double) * (size_t)n;
+  if (cost_train) CU(cudaMemcpyAsync(cost_train, f.cost_train, bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (cost_dev) CU(cudaMemcpyAsync(cost_dev, f.cost_dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (metric_train) CU(cudaMemcpyAsync(metric_train, f.metric_train, bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (metric_dev) CU(cudaMemcpyAsync(metric_dev, f.metric_dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_params_all(rfb_model* m, int n, float* b_all, double* icpt_all) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  Fit& f = m->fit;
+  if (!f.active) return fail(RFB_ERR_STATE, "no fit in progress");
+  if (n < 0 || n > f.executed) return fail(RFB_ERR_INVALID, "asked for %d iterations, %d executed", n, f.executed);
+  rfb_engine* e = m->e;
+  const Plan& p = m->plan;
+  TRY(use_device(e));
+  if (b_all && p.P > 0)
+    CU(cudaMemcpyAsync(b_all, f.ring_b, sizeof(float) * (size_t)n * p.P, cudaMemcpyDeviceToHost, e->stream));
+  if (icpt_all)
+    CU(cudaMemcpyAsync(icpt_all, f.ring_ic, sizeof(double) * (size_t)n * (p.F + 1), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_params_at(rfb_model* m, int i, float* b, double* intercepts) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  Fit& f = m->fit;
+  if (!f.active) return fail(RFB_ERR_STATE, "no fit in progress");
+  if (i < 0 || i >= f.executed) return fail(RFB_ERR_INVALID, "iteration %d was not executed", i);
+  rfb_engine* e = m->e;
+  const Plan& p = m->plan;
+  TRY(use_device(e));
+  if (b && p.P > 0)
+    CU(cudaMemcpyAsync(b, f.ring_b + (size_t)i * p.P, sizeof(float) * p.P, cudaMemcpyDeviceToHost, e->stream));
+  if (intercepts)
+    CU(cudaMemcpyAsync(intercepts, f.ring_ic + (size_t)i * (p.F + 1), sizeof(double) * (p.F + 1),
+                       cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_predictions(rfb_model* m, int kind, float* r_out) {
+  if (!m || !r_out) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind != RFB_KIND_TRAIN && kind != RFB_KIND_DEV) return fail(RFB_ERR_INVALID, "bad kind");
+  Fit& f = m->fit;
+  if (!f.active || !f.finished) return fail(RFB_ERR_STATE, "rfb_fit_finish has not been called");
+  DataSet& ds = m->data[kind];
+  if (!ds.r_buf) return fail(RFB_ERR_STATE, "no predictions for kind %d", kind);
+  TRY(use_device(m->e));
+  CU(cudaMemcpyAsync(r_out, ds.r_buf, sizeof(float) * (size_t)ds.n, cudaMemcpyDeviceToHost, m->e->stream));
+  CU(cudaStreamSynchronize(m->e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_end(rfb_model* m) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  TRY(use_device(m->e));
+  CU(cudaStreamSynchronize(m->e->stream));
+  // keep the final parameters as the model's current ones
+  if (m->fit.active && m->plan.ok) {
+    CU(cudaMemcpy(m->host_b.data(), m->cur.theta, sizeof(float) * m->plan.P, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(m->host_ic.data(), m->cur.ic, sizeof(double) * (m->plan.F + 1), cudaMemcpyDeviceToHost));
+  }
+  return fit_release(m);
+}

@@ -1,0 +1,252 @@
+"""Python handles over the C ABI: engine (one per GPU), design blocks, device model."""
+
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def as_f32(x):
+    """-> (pointer, on_device, keepalive, shape) for a float32 C-contiguous array / CUDA tensor."""
+    if _is_cuda_tensor(x):
+        import torch
+
+        t = x.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(torch.float32).contiguous()
+        return C.c_void_p(t.data_ptr()), 1, t, tuple(t.shape)
+    a = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+    return a.ctypes.data_as(C.c_void_p), 0, a, a.shape
+
+
+class Engine:
+    """One CUDA device + stream (+ NCCL communicator).  Use `Engine.get()`."""
+
+    _instances = {}
+
+    def __init__(self, device):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.rfb_engine_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+        self.rank, self.world = 0, 1
+        self._finalizer = weakref.finalize(self, self.lib.rfb_engine_destroy, h)
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("RFB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if device not in cls._instances:
+            cls._instances[device] = cls(device)
+        return cls._instances[device]
+
+    def synchronize(self):
+        check(self.lib.rfb_engine_synchronize(self.handle))
+
+    @property
+    def launch_count(self):
+        n = C.c_int64()
+        check(self.lib.rfb_engine_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    @property
+    def stream(self):
+        s = C.c_uint64()
+        check(self.lib.rfb_engine_stream(self.handle, C.byref(s)))
+        return s.value
+
+    def init_distributed(self):
+        """Join the ranks of an initialised `torch.distributed` process group with NCCL.
+
+        torch.distributed is only the bootstrap (it broadcasts the 128-byte NCCL id); the
+        per-iteration all-reduce is issued by the engine itself inside its CUDA graph."""
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size() == 1 or self.world > 1:
+            return self
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = (C.c_char * 128)()
+        if rank == 0:
+            check(self.lib.rfb_comm_unique_id(uid))
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=0)
+        buf = (C.c_char * 128).from_buffer_copy(box[0])
+        check(self.lib.rfb_engine_comm_init(self.handle, buf, rank, world))
+        self.rank, self.world = rank, world
+        return self
+
+    def allreduce_f64(self, values):
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        check(self.lib.rfb_engine_allreduce_f64(self.handle, a.ctypes.data_as(_lib._dp), a.size))
+        return a
+
+
+class Block:
+    """A projected design block XS_f resident in HBM: float32 (n_rows, n_cols)."""
+
+    def __init__(self, engine, n_rows, n_cols):
+        self.engine = engine
+        self.lib = engine.lib
+        h = C.c_void_p()
+        check(self.lib.rfb_block_create(engine.handle, int(n_rows), int(n_cols), C.byref(h)))
+        self.handle = h
+        self.shape = (int(n_rows), int(n_cols))
+        self.dtype = np.dtype(np.float32)
+        self._finalizer = weakref.finalize(self, self.lib.rfb_block_destroy, h)
+
+    @property
+    def ld(self):
+        ld = C.c_int64()
+        check(self.lib.rfb_block_shape(self.handle, None, None, C.byref(ld)))
+        return ld.value
+
+    @property
+    def device_ptr(self):
+        p = C.c_uint64()
+        check(self.lib.rfb_block_device_ptr(self.handle, C.byref(p)))
+        return p.value
+
+    def project(self, stim, *, dst_row0, n_out, col0, src0, n_raw_total, n_pix, first_t, nlag,
+                shift, St, Sxy):
+        """Fused lag + spline projection of raw rows into block rows (K1)."""
+        ptr, on_dev, keep, shape = as_f32(stim)
+        n_src = int(shape[0]) if len(shape) else 0
+        St = np.ascontiguousarray(St, dtype=np.float32)
+        df_t = St.shape[1]
+        if Sxy is not None:
+            Sxy = np.ascontiguousarray(Sxy, dtype=np.float32)
+            n_q = Sxy.shape[1]
+            sxy_ptr = Sxy.ctypes.data_as(C.c_void_p)
+        else:
+            n_q, sxy_ptr = 1, None
+        check(self.lib.rfb_block_project(
+            self.handle, int(dst_row0), int(n_out), int(col0), ptr, on_dev, int(src0), n_src,
+            int(n_raw_total), int(n_pix), int(first_t), int(nlag), int(shift),
+            St.ctypes.data_as(C.c_void_p), int(df_t), sxy_ptr, int(n_q)))
+        del keep
+
+    def write(self, row0, data):
+        ptr, on_dev, keep, shape = as_f32(data)
+        check(self.lib.rfb_block_write(self.handle, int(row0), int(shape[0]), ptr, on_dev))
+        del keep
+
+    def read(self, row0=0, n=None):
+        n = self.shape[0] - row0 if n is None else n
+        out = np.empty((n, self.shape[1]), dtype=np.float32)
+        check(self.lib.rfb_block_read(self.handle, int(row0), int(n), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # NumPy interoperability: np.asarray(model.XS['train']['stimulus']) copies the block back
+    def __array__(self, dtype=None, copy=None):
+        a = self.read()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __matmul__(self, other):
+        return np.asarray(self) @ np.asarray(other)
+
+
+class DeviceModel:
+    """rfb_model handle: filters, bound data, parameters, the fit loop."""
+
+    def __init__(self, engine, distr, output_nl):
+        self.engine = engine
+        self.lib = engine.lib
+        h = C.c_void_p()
+        check(self.lib.rfb_model_create(engine.handle, _lib.DISTR[distr], _lib.NL[output_nl],
+                                        C.byref(h)))
+        self.handle = h
+        self._keep = {}
+        self._finalizer = weakref.finalize(self, self.lib.rfb_model_destroy, h)
+
+    def clear_filters(self):
+        check(self.lib.rfb_model_clear_filters(self.handle))
+
+    def add_filter(self, slot, nl, n_coef):
+        return check(self.lib.rfb_model_add_filter(self.handle, int(slot), _lib.NL[nl], int(n_coef)))
+
+    def set_data(self, kind, blocks, y, n):
+        arr = (C.c_void_p * len(blocks))(*[b.handle.value if b is not None else None for b in blocks])
+        if y is None:
+            ptr, on_dev, keep = None, 0, None
+        else:
+            ptr, on_dev, keep, _ = as_f32(y)
+        check(self.lib.rfb_model_set_data(self.handle, _lib.KIND[kind], len(blocks), arr, ptr,
+                                          on_dev, int(n)))
+        self._keep[kind] = list(blocks)      # blocks must outlive the binding
+        del keep
+
+    def n_params(self):
+        a, b = C.c_int(), C.c_int()
+        check(self.lib.rfb_model_n_params(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_params(self, b, icpt):
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        icpt = np.ascontiguousarray(icpt, dtype=np.float64)
+        check(self.lib.rfb_model_set_params(self.handle, b.ctypes.data_as(C.c_void_p),
+                                            icpt.ctypes.data_as(C.c_void_p)))
+
+    def eval(self, kind, b=None, icpt=None, want_r=False, n=None):
+        sums = np.zeros(_lib.N_SUMS, dtype=np.float64)
+        r = np.empty(n, dtype=np.float32) if want_r else None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            icpt = np.ascontiguousarray(icpt, dtype=np.float64)
+        check(self.lib.rfb_model_eval(
+            self.handle, _lib.KIND[kind],
+            b.ctypes.data_as(C.c_void_p) if b is not None else None,
+            icpt.ctypes.data_as(C.c_void_p) if b is not None else None,
+            r.ctypes.data_as(C.c_void_p) if want_r else None,
+            sums.ctypes.data_as(C.c_void_p)))
+        return r, sums
+
+    # ---- fit loop ------------------------------------------------------------------------
+    def fit_begin(self, step_sizes, alpha, beta, metric):
+        steps = np.ascontiguousarray(step_sizes, dtype=np.float64)
+        check(self.lib.rfb_fit_begin(self.handle, steps.size, steps.ctypes.data_as(C.c_void_p),
+                                     float(alpha), float(beta), _lib.METRIC[metric]))
+
+    def fit_run(self, n):
+        check(self.lib.rfb_fit_run(self.handle, int(n)))
+
+    def fit_run_timed(self, n):
+        """-> mean ms of (train sweep, dev sweep, reduction + all-reduce, update) over n iterations."""
+        ms = np.zeros(4, dtype=np.float64)
+        check(self.lib.rfb_fit_run_timed(self.handle, int(n), ms.ctypes.data_as(_lib._dp)))
+        return ms
+
+    def fit_finish(self, i_last):
+        check(self.lib.rfb_fit_finish(self.handle, int(i_last)))
+
+    def fit_traces(self, n):
+        out = [np.empty(n, dtype=np.float64) for _ in range(4)]
+        check(self.lib.rfb_fit_traces(self.handle, int(n), *[o.ctypes.data_as(C.c_void_p) for o in out]))
+        return out
+
+    def fit_params_all(self, n):
+        P, K = self.n_params()
+        b = np.empty((n, P), dtype=np.float32)
+        ic = np.empty((n, K), dtype=np.float64)
+        check(self.lib.rfb_fit_params_all(self.handle, int(n), b.ctypes.data_as(C.c_void_p),
+                                          ic.ctypes.data_as(C.c_void_p)))
+        return b, ic
+
+    def fit_predictions(self, kind, n):
+        r = np.empty(n, dtype=np.float32)
+        check(self.lib.rfb_fit_predictions(self.handle, _lib.KIND[kind], r.ctypes.data_as(C.c_void_p)))
+        return r
+
+    def fit_end(self):
+        check(self.lib.rfb_fit_end(self.handle))

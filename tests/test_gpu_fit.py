@@ -1,0 +1,299 @@
+"""GPU parity: the streaming sweep + Adam loop (K2/K3/K4) against the oracle.
+
+Tolerances are the north star's: per-iteration train/dev loss within 1e-5 relative, final
+filter weights within 1e-4 relative (summation order differs), measured against the fp64
+oracle; the oracle's own fp32 mode is run alongside to show the same distance.
+"""
+
+import numpy as np
+import pytest
+
+from oracle.glm import OracleGLM
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+WEIGHT_RTOL = 1e-4
+
+
+def _pair(distr, out_nl, dtype=np.float64):
+    from rfest_b200 import GLM
+
+    return GLM(distr=distr, output_nonlinearity=out_nl), OracleGLM(distr=distr, output_nonlinearity=out_nl, dtype=dtype)
+
+
+def _same_p0(models, scale=0.1, seed=77, icpt=None):
+    ref = models[0]
+    for k, name in enumerate(ref.filter_names):
+        shape = np.asarray(ref.p0[name]).shape
+        b = (scale * np.random.default_rng(seed + k).standard_normal(shape)).astype(np.float32)
+        for m in models:
+            m.p0[name] = b.astype(m.dtype)
+            if icpt is not None:
+                m.p0["intercept"][name] = icpt * (k + 1)
+    if icpt is not None:
+        for m in models:
+            m.p0["intercept"]["global"] = -2 * icpt
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def _wrel(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def _compare_fit(g, o, check_dev, metric_tol=1e-5):
+    assert len(g.cost_train) == len(o.cost_train)
+    assert _rel(g.cost_train, o.cost_train) < LOSS_RTOL
+    if check_dev:
+        assert _rel(g.cost_dev, o.cost_dev) < LOSS_RTOL
+        assert np.max(np.abs(g.metric_dev - o.metric_dev)) < metric_tol
+    assert np.max(np.abs(g.metric_train - o.metric_train)) < metric_tol
+    last_g, last_o = g.all_params[-1], o.all_params[-1]
+    for name in o.filter_names:
+        assert _wrel(last_g[name], last_o[name]) < WEIGHT_RTOL
+        assert abs(last_g["intercept"][name] - float(last_o["intercept"][name])) < 1e-4 * max(
+            1.0, abs(float(last_o["intercept"][name])))
+    assert abs(last_g["intercept"]["global"] - float(last_o["intercept"]["global"])) < 1e-4
+    for kind in o.y_pred["opt"]:
+        assert _wrel(g.y_pred["opt"][kind], o.y_pred["opt"][kind]) < 1e-4
+
+
+def test_forward_and_cost_match_oracle():
+    stim, y, _ = helpers.lnp_data(3001, (8, 5, 4), seed=9)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", name="stimulus")
+        m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(method="random", random_seed=1)
+    _same_p0([o, g], icpt=0.05)
+    for m in (g, o):
+        m.alpha, m.beta = 0.5, 0.01
+        m.y["train"] = np.asarray(y)[m.burn_in:].astype(m.dtype)
+    g._dirty = True
+    r_g, r_o = g.forwardpass(g.p0, "train"), o.forwardpass(o.p0, "train")
+    assert r_g.shape == r_o.shape and r_g.dtype == np.float32
+    assert _wrel(r_g, r_o) < 1e-6
+    assert abs(g.cost(g.p0, "train") - o.cost(o.p0, "train")) < 1e-6 * abs(o.cost(o.p0, "train"))
+    assert abs(g.cost(g.p0, "train", penalize=False) - o.cost(o.p0, "train", penalize=False)) < 1e-6 * abs(
+        o.cost(o.p0, "train", penalize=False))
+
+
+CONFIGS = [
+    # distr, out_nl, filt_nl, subunits, alpha, beta, step, metric, history, dev
+    ("poisson", "softplus", "none", 1, 1.0, 0.01, 0.05, "corrcoef", True, True),
+    ("poisson", "exponential", "none", 1, 0.5, 0.01, 0.01, "r2", True, False),
+    ("gaussian", "none", "none", 1, 1.0, 0.001, 0.03, "mse", True, True),
+    ("gaussian", "none", "none", 2, 1.0, 0.001, 0.03, "mse", False, False),
+    ("poisson", "softplus", "softplus", 4, 0.5, 0.01, 0.02, "corrcoef", True, True),
+    ("gaussian", "softplus", "tanh", 2, 0.0, 0.01, 0.02, "r2", False, True),
+    ("poisson", "softplus", "sigmoid", 1, 1.0, 0.0, 0.02, "corrcoef", True, False),
+    ("gaussian", "relu", "leaky_relu", 1, 0.3, 0.02, 0.01, "mse", True, True),
+]
+
+
+@pytest.mark.parametrize("distr,out_nl,filt_nl,subunits,alpha,beta,step,metric,history,dev", CONFIGS)
+def test_fit_trajectory_matches_oracle(distr, out_nl, filt_nl, subunits, alpha, beta, step, metric,
+                                       history, dev):
+    n = 2603                      # not a multiple of any tile size
+    stim, y, _ = helpers.lnp_data(n, (8, 5, 4), seed=31)
+    if distr == "gaussian":
+        y = (y - y.mean()).astype(np.float32)
+    n_tr = 2000 if dev else n
+    g, o = _pair(distr, out_nl)
+    for m in (g, o):
+        m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr",
+                            filter_nonlinearity=filt_nl, name="stimulus")
+        if dev:
+            m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
+        if history:
+            m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+            if dev:
+                m.add_design_matrix(y[n_tr:], name="history", kind="dev")
+        m.initialize(num_subunits=subunits, method="random", random_seed=3)
+    _same_p0([o, g], icpt=0.02)
+    fit_y = {"train": y[:n_tr]}
+    if dev:
+        fit_y["dev"] = y[n_tr:]
+    for m in (g, o):
+        m.fit(y=fit_y, num_iters=60, alpha=alpha, beta=beta, metric=metric, step_size=step,
+              tolerance=0, verbose=0)
+    assert g.filter_names == o.filter_names
+    _compare_fit(g, o, dev)
+    assert g.best_iteration == o.best_iteration or abs(
+        (o.cost_dev if dev else o.cost_train)[g.best_iteration]
+        - (o.cost_dev if dev else o.cost_train)[o.best_iteration]) < 1e-5 * abs(o.cost_train[0])
+
+
+def test_readme_recipe_config1():
+    """BASELINE config 1 / the reference README: 1-D LNP, dims [25] df [8] + history [20]/[8]
+    shift 1, ~20k samples, step_size 0.1, beta 0.01 (alpha defaults to 1), 80/20 train/dev."""
+    stim, y, _ = helpers.lnp_data(20000, (25,), seed=2046)
+    n_tr = 16000
+    g, o64 = _pair("poisson", "softplus")
+    o32 = OracleGLM("poisson", "softplus", dtype=np.float32)
+    models = (g, o64, o32)
+    for m in models:
+        m.add_design_matrix(stim[:n_tr], dims=[25], df=[8], smooth="cr", name="stimulus")
+        m.add_design_matrix(y[:n_tr], dims=[20], df=[8], smooth="cr", shift=1, name="history")
+        m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
+        m.add_design_matrix(y[n_tr:], name="history", kind="dev")
+        m.initialize(num_subunits=1, dt=0.033, method="random", random_seed=2046)
+    _same_p0([o64, o32, g])
+    iters = 400
+    for m in models:
+        m.fit(y={"train": y[:n_tr], "dev": y[n_tr:]}, num_iters=iters, verbose=0, step_size=0.1,
+              beta=0.01, tolerance=0)
+    _compare_fit(g, o64, True)
+    # the engine is at least as close to fp64 as the fp32 restatement of the reference is
+    d_engine = _rel(g.cost_train, o64.cost_train)
+    d_fp32 = _rel(o32.cost_train, o64.cost_train)
+    assert d_engine < max(4 * d_fp32, 2e-6)
+    assert g.cost_train[-1] < 0.6 * g.cost_train[0]
+
+
+def test_3d_lnp_shape_of_config2_small():
+    """Config 2/3 shapes (dims [25,20,15], df [8,6,6] + history [20]/[8]) at a CPU-checkable n."""
+    n = 1500
+    rng = np.random.default_rng(5)
+    stim = rng.standard_normal((n, 20, 15)).astype(np.float32)
+    y = rng.poisson(0.3, n).astype(np.float32)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[25, 20, 15], df=[8, 6, 6], smooth="cr", name="stimulus")
+        m.add_design_matrix(y, dims=[20], df=[8], smooth="cr", shift=1, name="history")
+        m.initialize(method="random", random_seed=2046)
+    _same_p0([o, g], scale=0.1)
+    for m in (g, o):
+        m.fit(y=y, num_iters=25, verbose=0, step_size=0.01, beta=0.01, tolerance=0)
+    assert g.n_features == {"stimulus": 288, "history": 8}
+    _compare_fit(g, o, False)
+
+
+def test_wide_design_config5_shape_small():
+    """Config 5 shape: Gaussian, dims [40,32,32] df [12,10,10] (1200 coefficients)."""
+    n = 700
+    rng = np.random.default_rng(6)
+    stim = rng.standard_normal((n, 32, 32)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    g, o = _pair("gaussian", "none")
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[40, 32, 32], df=[12, 10, 10], smooth="cr", name="stimulus")
+        m.initialize(method="random", random_seed=1)
+    _same_p0([o, g], scale=0.05)
+    for m in (g, o):
+        m.fit(y=y, num_iters=15, verbose=0, step_size=0.01, beta=0.001, tolerance=0, metric="r2")
+    assert g.n_features["stimulus"] == 1200
+    _compare_fit(g, o, False, metric_tol=1e-4)
+
+
+def test_trace_semantics_and_predictions():
+    stim, y, _ = helpers.lnp_data(1500, (6, 3, 3), seed=4)
+    from rfest_b200 import GLM
+
+    m = GLM(distr="poisson", output_nonlinearity="softplus")
+    m.add_design_matrix(stim[:1000], dims=[6, 3, 3], df=[3, 3, 3], smooth="cr", name="stimulus")
+    m.add_design_matrix(stim[1000:], name="stimulus", kind="dev")
+    m.initialize(method="random", random_seed=3)
+    m.p0["stimulus"] = (0.05 * m.p0["stimulus"]).astype(np.float32)
+    m.fit(y={"train": y[:1000], "dev": y[1000:]}, num_iters=6, step_size=0.01, beta=0.01,
+          verbose=0, tolerance=0, metric="r2")
+    assert len(m.cost_train) == 6 and len(m.all_params) == 6
+    assert np.isclose(m.cost_train[0], m.cost(m.p0, "train"), rtol=1e-6)
+    for i in range(5):      # cost_train[i+1] is the cost at the parameters after update i
+        assert np.isclose(m.cost_train[i + 1], m.cost(m.all_params[i], "train"), rtol=1e-6)
+    for i in range(6):      # dev cost / metrics are post-update, unpenalised
+        assert np.isclose(m.cost_dev[i], m.cost(m.all_params[i], "dev", penalize=False), rtol=1e-6)
+        rp = m.forwardpass(m.all_params[i], "train")
+        assert np.isclose(m.metric_train[i], m.compute_score(m.y["train"], rp, "r2"), atol=1e-5)
+    np.testing.assert_allclose(m.y_pred["opt"]["train"], m.forwardpass(m.all_params[-1], "train"), rtol=1e-6)
+    np.testing.assert_allclose(m.y_pred["opt"]["dev"], m.forwardpass(m.all_params[-1], "dev"), rtol=1e-6)
+    assert m.return_model == "best_dev_cost" and m.best_iteration == int(np.argmin(m.cost_dev))
+    assert m.train_stop == "maxiter_stop"
+    assert set(m.w["opt"]) == {"stimulus"} and m.w["opt"]["stimulus"].shape == (54, 1)
+
+
+def test_early_stopping_and_model_selection_match_oracle():
+    stim, y, _ = helpers.lnp_data(1400, (6, 3, 3), seed=12)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim[:1000], dims=[6, 3, 3], df=[3, 3, 3], smooth="cr", name="stimulus")
+        m.add_design_matrix(stim[1000:], name="stimulus", kind="dev")
+        m.initialize(method="random", random_seed=3)
+    _same_p0([o, g], scale=0.3)
+    for m in (g, o):       # large steps: the dev cost starts rising soon
+        m.fit(y={"train": y[:1000], "dev": y[1000:]}, num_iters=400, step_size=0.05, beta=0.0,
+              verbose=0, tolerance=5, min_iters=20, metric="corrcoef")
+    assert g.train_stop == o.train_stop
+    assert len(g.cost_train) == len(o.cost_train)
+    assert g.best_iteration == o.best_iteration
+    assert _rel(g.cost_dev, o.cost_dev) < LOSS_RTOL
+    for rm in ("last", "best_train_cost", "best_dev_metric", "best_train_metric"):
+        for m in (g, o):
+            m.fit(y={"train": y[:1000], "dev": y[1000:]}, num_iters=40, step_size=0.05, beta=0.0,
+                  verbose=0, tolerance=0, metric="corrcoef", return_model=rm)
+        assert g.best_iteration == o.best_iteration and g.return_model == rm
+
+
+def test_step_size_schedule_and_refit():
+    stim, y, _ = helpers.lnp_data(1200, (6, 3, 3), seed=2)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[6, 3, 3], df=[3, 3, 3], smooth="cr", name="stimulus")
+        m.initialize(method="random", random_seed=3)
+    _same_p0([o, g], scale=0.1)
+    sched = lambda i: 0.05 * 0.97 ** i                                  # noqa: E731
+    for m in (g, o):
+        m.fit(y=y, num_iters=30, step_size=sched, beta=0.01, verbose=0, tolerance=0)
+    _compare_fit(g, o, False)
+    first = g.cost_train.copy()
+    g.fit(y=y, num_iters=30, step_size=sched, beta=0.01, verbose=0, tolerance=0)
+    assert np.array_equal(first, g.cost_train)                           # deterministic, no atomics
+
+
+def test_predict_and_score():
+    w_true, X, y, dims = helpers.data_3d_stim()
+    tr, dv, te = helpers.split(X, y, 0.6, 0.2)
+    df = helpers.df_rule(dims)
+    g, o = _pair("gaussian", "none")
+    for m in (g, o):
+        m.add_design_matrix(tr[0], dims=list(dims), df=df, smooth="cr", name="stimulus")
+        m.add_design_matrix(dv[0], name="stimulus", kind="dev")
+        m.add_design_matrix(tr[1], dims=[5], df=[3], smooth="cr", name="history")
+        m.add_design_matrix(dv[1], name="history", kind="dev")
+        m.initialize(method="random", random_seed=42)
+    _same_p0([o, g], scale=0.01)
+    for m in (g, o):
+        m.fit(y={"train": tr[1], "dev": dv[1]}, num_iters=200, verbose=0, step_size=0.03,
+              beta=0.001, metric="mse", tolerance=0)
+    for Xs, ys in ((tr, tr[1]), (dv, dv[1]), (te, te[1])):
+        sg = g.score({"stimulus": Xs[0], "history": Xs[1]}, ys)
+        so = o.score({"stimulus": Xs[0], "history": Xs[1]}, ys)
+        assert abs(sg - so) < 1e-4
+    assert g.score({"stimulus": te[0], "history": te[1]}, te[1]) > 0.2        # reference threshold
+    # only the stimulus filter has test data: the history filter drops out (_glm.py:555)
+    sg, pg = g.score(te[0], te[1], return_prediction=True)
+    so, po = o.score(te[0], te[1], return_prediction=True)
+    assert _wrel(pg, po) < 1e-4 and abs(sg - so) < 1e-4
+    mse_w = np.mean((helpers.uvec(g.w["opt"]["stimulus"]).ravel() - helpers.uvec(w_true.flatten())) ** 2)
+    assert mse_w < 0.01                                                       # tests/test_glm.py:87
+
+
+def test_nan_raises_like_debug_nans():
+    stim, y, _ = helpers.lnp_data(600, (6,), seed=1)
+    from rfest_b200 import GLM
+
+    m = GLM(distr="poisson", output_nonlinearity="exponential")
+    m.add_design_matrix(stim, dims=[6], df=[3], smooth="cr", name="stimulus")
+    m.initialize(method="random", random_seed=0)
+    m.p0["stimulus"] = np.full_like(m.p0["stimulus"], np.nan)
+    with pytest.raises(FloatingPointError):
+        m.fit(y=y, num_iters=3, verbose=0, tolerance=0)
+    with pytest.raises(ValueError):
+        GLM().fit(num_iters=1)
