@@ -22,6 +22,9 @@ def as_f32(x):
         t = x.detach()
         if t.dtype != torch.float32 or not t.is_contiguous():
             t = t.to(torch.float32).contiguous()
+        # the engine runs on its own stream: whatever torch still has in flight for this
+        # tensor must have landed before the pointer is handed over
+        torch.cuda.current_stream(t.device).synchronize()
         return C.c_void_p(t.data_ptr()), 1, t, tuple(t.shape)
     a = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
     return a.ctypes.data_as(C.c_void_p), 0, a, a.shape
@@ -144,6 +147,21 @@ class Block:
         out = np.empty((n, self.shape[1]), dtype=np.float32)
         check(self.lib.rfb_block_read(self.handle, int(row0), int(n), out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def as_torch(self):
+        """Zero-copy torch view (n_rows, n_cols) of the block's HBM storage (strided by ld)."""
+        import torch
+
+        class _View:
+            pass
+
+        v = _View()
+        v.__cuda_array_interface__ = {
+            "shape": self.shape, "typestr": "<f4", "data": (self.device_ptr, False), "version": 2,
+            "strides": (self.ld * 4, 4)}
+        t = torch.as_tensor(v, device=f"cuda:{self.engine.device}")
+        t._rfb_keepalive = self
+        return t
 
     # NumPy interoperability: np.asarray(model.XS['train']['stimulus']) copies the block back
     def __array__(self, dtype=None, copy=None):

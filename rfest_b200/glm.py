@@ -32,6 +32,14 @@ from .splines import KronBasis
 __all__ = ["GLM"]
 
 
+def _is_row_source(x):
+    """A row source streams a recording that is too large (or not yet materialised) to hand
+    over as one array: `shape` = (n_raw, *frame) and `rows(lo, hi)` -> float32 array or CUDA
+    tensor with raw rows [lo, hi).  np.memmap-backed files, generators and per-rank shards
+    all fit this; the engine only ever asks for the rows it projects next."""
+    return hasattr(x, "rows") and callable(x.rows) and hasattr(x, "shape")
+
+
 class LaggedDesign:
     """Stand-in for the reference's `self.X[kind][name]` (the n x nlag*n_pix matrix that the
     engine never materialises).  Knows its shape; `materialize()` builds it on the host for
@@ -48,6 +56,8 @@ class LaggedDesign:
         return self.shape[0]
 
     def materialize(self, dtype=np.float32):
+        if _is_row_source(self._raw):
+            self._raw = self._raw.rows(0, self._raw.shape[0])
         raw = self._raw.cpu().numpy() if _is_cuda_tensor(self._raw) else np.asarray(self._raw)
         flat = raw.reshape(raw.shape[0], -1)
         if not self.lag:
@@ -159,7 +169,10 @@ class GLM:
         if filter_nonlinearity not in _lib.NL:
             raise NotImplementedError(
                 f"Input filter nonlinearity `{filter_nonlinearity}` is not supported.")
-        if not _is_cuda_tensor(X):
+        streamed = _is_row_source(X)
+        if streamed and global_rows is not None:
+            raise ValueError("a row source already addresses the whole recording; drop `global_rows`")
+        if not streamed and not _is_cuda_tensor(X):
             X = np.asarray(X)
             if X.dtype != np.float32:
                 X = X.astype(np.float32)                                       # _glm.py:231-234
@@ -236,13 +249,24 @@ class GLM:
         need_lo, need_hi = source_rows(first_t, n_out, nlag, eff_shift, n_raw)
 
         block = Block(self.engine, n_out, n_cols)
-        if global_rows is None and self.engine.world > 1 and need_hi > need_lo:
-            X_part, part0 = X[need_lo:need_hi], need_lo          # ship only what this rank reads
+        common = dict(col0=0, n_raw_total=n_raw, n_pix=n_pix, nlag=nlag, shift=eff_shift, St=St, Sxy=Sxy)
+        if streamed:
+            # pull only the raw rows each slab of design rows reads (this rank's rows + halo)
+            step = int(getattr(X, "chunk_rows", 1 << 18))
+            for k0 in range(0, n_out, step):
+                kc = min(step, n_out - k0)
+                s_lo, s_hi = source_rows(first_t + k0, kc, nlag, eff_shift, n_raw)
+                rows = X.rows(s_lo, s_hi)
+                rows = rows.reshape(rows.shape[0], -1) if len(rows.shape) != 2 else rows
+                block.project(rows, dst_row0=k0, n_out=kc, src0=s_lo, first_t=first_t + k0, **common)
+                del rows
         else:
-            X_part, part0 = X, src0
-        X_part = X_part.reshape(X_part.shape[0], -1) if len(X_part.shape) != 2 else X_part
-        block.project(X_part, dst_row0=0, n_out=n_out, col0=0, src0=part0, n_raw_total=n_raw,
-                      n_pix=n_pix, first_t=first_t, nlag=nlag, shift=eff_shift, St=St, Sxy=Sxy)
+            if global_rows is None and self.engine.world > 1 and need_hi > need_lo:
+                X_part, part0 = X[need_lo:need_hi], need_lo      # ship only what this rank reads
+            else:
+                X_part, part0 = X, src0
+            X_part = X_part.reshape(X_part.shape[0], -1) if len(X_part.shape) != 2 else X_part
+            block.project(X_part, dst_row0=0, n_out=n_out, src0=part0, first_t=first_t, **common)
 
         self.X[kind][name] = LaggedDesign(X, nlag, eff_shift, burn, lag)
         self._blocks.setdefault(kind, {})[name] = block
