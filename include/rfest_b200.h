@@ -85,6 +85,11 @@ int rfb_engine_destroy(rfb_engine* e);
 int rfb_engine_synchronize(rfb_engine* e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches claim) */
 int rfb_engine_launch_count(rfb_engine* e, int64_t* out);
+/* Launch-shape knobs of the sweep kernel, applied to models (re)planned afterwards:
+ * "sweep_staged" (1 = rows staged through shared memory by cp.async.bulk, 0 = direct loads),
+ * "sweep_stages" (ring depth per warp), "sweep_warps" (warps per CTA), "sweep_ctas" (CTAs per
+ * SM, 0 = as many as fit).  Also read from RFB_SWEEP_* environment variables at creation. */
+int rfb_engine_set_option(rfb_engine* e, const char* key, int value);
 /* the engine's CUDA stream (cudaStream_t as an integer), for event timing by the caller */
 int rfb_engine_stream(rfb_engine* e, uint64_t* out);
 

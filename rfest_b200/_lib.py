@@ -39,6 +39,7 @@ SIGNATURES = {
     "rfb_engine_destroy": (_i, [_p]),
     "rfb_engine_synchronize": (_i, [_p]),
     "rfb_engine_launch_count": (_i, [_p, C.POINTER(_i64)]),
+    "rfb_engine_set_option": (_i, [_p, C.c_char_p, _i]),
     "rfb_engine_stream": (_i, [_p, C.POINTER(_u64)]),
     "rfb_comm_unique_id": (_i, [_p]),
     "rfb_engine_comm_init": (_i, [_p, _p, _i, _i]),

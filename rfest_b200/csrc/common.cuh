@@ -46,6 +46,7 @@ struct SweepArgs {
   double* cta_part;                 // [grid][NE] per-CTA partial sums (output)
   float* r_out;                     // optional [n_rows]
   int flush_tiles;                  // fp32 -> fp64 flush cadence, in tiles
+  int n_stages;                     // staged variant: depth of each warp's copy ring
 };
 
 __host__ __device__ inline int sweep_num_entries(int H, int n_chunks) {

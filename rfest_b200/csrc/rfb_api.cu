@@ -108,6 +108,11 @@ struct rfb_engine {
   void* comm = nullptr;
   int rank = 0, world = 1;
   Scratch stage, zbuf, stbuf, sxybuf, small;
+  // sweep launch shape (tunable: rfb_engine_set_option / RFB_SWEEP_* environment variables)
+  int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
+  int sweep_stages = 3;   // depth of each warp's copy ring
+  int sweep_warps = 4;    // warps per CTA
+  int sweep_ctas = 0;     // CTAs per SM (0: as many as fit)
 };
 
 static int scratch_reserve(rfb_engine* e, Scratch& s, size_t bytes) {
@@ -160,6 +165,9 @@ struct SweepBuffers {
   double* cta_part = nullptr;
   size_t warp_acc_bytes = 0, cta_part_bytes = 0;
   int grid = 0;
+  int threads = 0;
+  int staged = 0, stages = 0;
+  size_t smem = 0;
 };
 
 struct Plan {
@@ -229,19 +237,21 @@ struct rfb_model {
 typedef void (*SweepFn)(const SweepArgs);
 
 template <int H, int NCH, int RB>
-static SweepFn pick_bwd(bool bwd) {
-  return bwd ? (SweepFn)sweep_kernel<H, NCH, RB, true> : (SweepFn)sweep_kernel<H, NCH, RB, false>;
+static SweepFn pick_variant(bool bwd, bool staged) {
+  if (staged)
+    return bwd ? (SweepFn)sweep_kernel<H, NCH, RB, true, true> : (SweepFn)sweep_kernel<H, NCH, RB, false, true>;
+  return bwd ? (SweepFn)sweep_kernel<H, NCH, RB, true, false> : (SweepFn)sweep_kernel<H, NCH, RB, false, false>;
 }
 
 static int template_heads(int H) { return H <= 1 ? 1 : H <= 2 ? 2 : H <= 3 ? 3 : 5; }
 static int template_chunks(int nch) { return nch <= 1 ? 1 : nch <= 3 ? 3 : nch <= 5 ? 5 : 10; }
 
 // rows per tile for each (heads, chunks-per-lane) instance: bounded by registers
-static SweepFn sweep_instance(int Ht, int NCH, bool bwd, int* RB) {
-#define INST(h, c, rb)                \
-  if (Ht == h && NCH == c) {          \
-    *RB = rb;                         \
-    return pick_bwd<h, c, rb>(bwd);   \
+static SweepFn sweep_instance(int Ht, int NCH, bool bwd, bool staged, int* RB) {
+#define INST(h, c, rb)                          \
+  if (Ht == h && NCH == c) {                    \
+    *RB = rb;                                   \
+    return pick_variant<h, c, rb>(bwd, staged); \
   }
   INST(1, 1, 8) INST(1, 3, 8) INST(1, 5, 4) INST(1, 10, 2)
   INST(2, 1, 8) INST(2, 3, 8) INST(2, 5, 4) INST(2, 10, 1)
@@ -295,7 +305,7 @@ static int build_plan(rfb_model* m) {
   if (nch > 10)
     return fail(RFB_ERR_UNSUPPORTED, "%d design columns per sample (max 1280)", p.ctot);
   p.NCH = template_chunks(nch);
-  if (!sweep_instance(p.Ht, p.NCH, true, &p.RB)) {
+  if (!sweep_instance(p.Ht, p.NCH, true, false, &p.RB)) {
     // fall back to a larger head template that exists for this width
     return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel for %d heads x %d columns", p.H, p.ctot);
   }
@@ -403,21 +413,50 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
   SweepBuffers& sb = m->sb[kind];
   if (sb.grid != 0) return RFB_OK;
   int RB = 0;
-  SweepFn fn = sweep_instance(p.Ht, p.NCH, true, &RB);
-  if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
+  const int warps = std::min(std::max(e->sweep_warps, 1), kSweepMaxThreads / 32);
+  const int threads = warps * 32;
+  int staged = e->sweep_staged ? 1 : 0;
+  int stages = std::max(e->sweep_stages, 1);
   int occ = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSweepThreads, 0));
-  if (occ < 1) occ = 1;
-  const int wpc = kSweepThreads / 32;
+  size_t smem = 0;
+  for (;;) {
+    smem = staged ? sweep_smem_bytes(warps, stages, p.RB, p.ctot) : 0;
+    occ = 0;
+    bool ok = true;
+    for (int bwd = 0; bwd < 2 && ok; ++bwd) {
+      SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd != 0, staged != 0, &RB);
+      if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
+      if (smem > 48 * 1024) {
+        cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) {
+          cudaGetLastError();
+          ok = false;
+          break;
+        }
+      }
+      int o = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, threads, smem));
+      if (bwd) occ = o;   // the gradient sweep decides the launch shape
+    }
+    if (ok && occ >= 1) break;
+    if (staged && stages > 2) { --stages; continue; }       // shallower ring
+    if (staged) { staged = 0; continue; }                   // rows too wide to stage: stream directly
+    return fail(RFB_ERR_CUDA, "sweep kernel does not fit on an SM");
+  }
+  if (e->sweep_ctas > 0) occ = std::min(occ, e->sweep_ctas);
   const int64_t ntiles = (ds.n + RB - 1) / RB;
   int64_t grid = (int64_t)e->num_sms * occ;
-  const int64_t need = (ntiles + wpc - 1) / wpc;
+  const int64_t need = (ntiles + warps - 1) / warps;
   if (grid > need) grid = std::max<int64_t>(need, 1);
-  sb.warp_acc_bytes = sizeof(double) * (size_t)grid * wpc * p.NE;
+  sb.warp_acc_bytes = sizeof(double) * (size_t)grid * warps * p.NE;
   sb.cta_part_bytes = sizeof(double) * (size_t)grid * p.NE;
   CU(cudaMalloc(&sb.warp_acc, sb.warp_acc_bytes));
   CU(cudaMalloc(&sb.cta_part, sb.cta_part_bytes));
   sb.grid = (int)grid;
+  sb.threads = threads;
+  sb.staged = staged;
+  sb.stages = stages;
+  sb.smem = smem;
   return RFB_OK;
 }
 
@@ -429,10 +468,10 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   DataSet& ds = m->data[kind];
   rfb_engine* e = m->e;
   int RB = 0;
-  SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd, &RB);
-  if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
   TRY(ensure_sweep_buffers(m, kind));
   SweepBuffers& sb = m->sb[kind];
+  SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, &RB);
+  if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
 
   SweepArgs a{};
   a.n_slots = p.n_slots;
@@ -456,7 +495,8 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   a.cta_part = sb.cta_part;
   a.r_out = r_out;
   a.flush_tiles = std::max(1, 256 / RB);
-  fn<<<sb.grid, kSweepThreads, 0, e->stream>>>(a);
+  a.n_stages = sb.stages;
+  fn<<<sb.grid, sb.threads, sb.smem, e->stream>>>(a);
   e->launches++;
   CU(cudaGetLastError());
   return RFB_OK;
@@ -503,7 +543,22 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   e->device = device;
   e->num_sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  if (const char* v = getenv("RFB_SWEEP_STAGED")) e->sweep_staged = atoi(v);
+  if (const char* v = getenv("RFB_SWEEP_STAGES")) e->sweep_stages = atoi(v);
+  if (const char* v = getenv("RFB_SWEEP_WARPS")) e->sweep_warps = atoi(v);
+  if (const char* v = getenv("RFB_SWEEP_CTAS")) e->sweep_ctas = atoi(v);
   *out = e;
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) {
+  if (!e || !key) return fail(RFB_ERR_INVALID, "NULL argument");
+  const std::string k(key);
+  if (k == "sweep_staged") e->sweep_staged = value;
+  else if (k == "sweep_stages") e->sweep_stages = value;
+  else if (k == "sweep_warps") e->sweep_warps = value;
+  else if (k == "sweep_ctas") e->sweep_ctas = value;
+  else return fail(RFB_ERR_INVALID, "unknown option '%s'", key);
   return RFB_OK;
 }
 

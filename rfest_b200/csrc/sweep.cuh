@@ -36,6 +36,45 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   return v;
 }
 
+// ---- bulk-async (TMA 1-D) staging helpers: cp.async.bulk + mbarrier, sm_90+ PTX ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// contiguous global -> shared copy by the copy engine, completion signalled on an mbarrier;
+// streamed data is marked evict-first in L2 (it is read exactly once per sweep)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
 // phi(x) and phi'(x).  GLM.fnl, rfest/GLM/_glm.py:103-170.  Softplus is the reference's
 // naive log(1 + exp(x)) + 1e-7 in fp32 (NOT log1p): for x < -16.6 it is exactly 1e-7.
 __device__ __forceinline__ void nl_eval(int kind, float x, float& f, float& d) {
@@ -111,11 +150,29 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   return v;
 }
 
-constexpr int kSweepThreads = 128;
+constexpr int kSweepMaxThreads = 128;
 
-template <int H, int NCH, int RB, bool BWD>
-__global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const __grid_constant__ SweepArgs a) {
+// resident CTAs per SM the compiler must leave registers for (staged variant: more warps to
+// overlap the per-tile arithmetic; the copy ring, not the warp count, hides HBM latency)
+__host__ __device__ constexpr int sweep_min_blocks(int H, int NCH, bool staged) {
+  return !staged ? 1 : (H * NCH <= 3 ? 3 : (H * NCH <= 6 ? 2 : 1));
+}
+
+// bytes of dynamic shared memory the staged variant needs
+__host__ __device__ inline size_t sweep_smem_bytes(int warps, int stages, int RB, int ctot) {
+  return (size_t)warps * stages * ((size_t)RB * ctot * sizeof(float) + sizeof(uint64_t));
+}
+
+// STAGED = false: rows go HBM -> registers with streaming 16-byte loads.
+// STAGED = true : every warp runs its own `n_stages`-deep ring of bulk-async copies (one
+//   contiguous RB x ld chunk per design block and tile), waits on the tile's mbarrier, pulls the
+//   rows into registers with conflict-free LDS.128 and immediately re-arms the buffer with the
+//   tile `n_stages` ahead -- the copy engine keeps the HBM pipe full while the warp computes.
+template <int H, int NCH, int RB, bool BWD, bool STAGED>
+__global__ void __launch_bounds__(kSweepMaxThreads, sweep_min_blocks(H, NCH, STAGED))
+sweep_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(RB >= 1 && RB <= 32 && (RB & (RB - 1)) == 0, "RB must be a power of two");
+  extern __shared__ __align__(128) unsigned char sweep_smem[];
   const int lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   const long long gw = (long long)blockIdx.x * wpc + (threadIdx.x >> 5);
@@ -126,6 +183,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const __grid_const
   // ---- column ownership -------------------------------------------------------------
   const float* cptr[NCH];
   long long cld[NCH];
+  int soff[NCH];   // staged: float offset of this lane's chunk inside a stage buffer
   bool cvalid[NCH];
   float4 w[H][NCH];
   float4 g[H][NCH];
@@ -135,12 +193,14 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const __grid_const
     cvalid[i] = c < a.n_chunks;
     cptr[i] = nullptr;
     cld[i] = 0;
+    soff[i] = 0;
     if (cvalid[i]) {
       int s = 0;
       while (s + 1 < a.n_slots && c >= a.slot_chunk0[s + 1]) ++s;
       cvalid[i] = a.slot_ptr[s] != nullptr;   // slot without a block in this data set
       cptr[i] = a.slot_ptr[s] + 4 * (c - a.slot_chunk0[s]);
       cld[i] = a.slot_ld[s];
+      soff[i] = RB * 4 * a.slot_chunk0[s] + 4 * (c - a.slot_chunk0[s]);
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -205,16 +265,68 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const __grid_const
   // ---- stream the rows ------------------------------------------------------------------
   const long long ntiles = (a.n_rows + RB - 1) / RB;
   const int myr = lane & (RB - 1);
-  for (long long tile = gw; tile < ntiles; tile += GW) {
+
+  // staged: this warp's ring of stage buffers and their mbarriers
+  const int NS = a.n_stages;
+  const int stage_floats = RB * ctot;
+  float* wbuf = nullptr;
+  uint64_t* bars = nullptr;
+  uint64_t policy = 0;
+  auto issue = [&](long long tile, int buf) {   // lane 0: arm the barrier, start the copies
+    const long long row0 = tile * RB;
+    const int rows = (int)((a.n_rows - row0 < RB) ? (a.n_rows - row0) : RB);
+    uint32_t bytes = 0;
+    for (int s = 0; s < a.n_slots; ++s)
+      if (a.slot_ptr[s] != nullptr) bytes += (uint32_t)(rows * a.slot_ld[s] * sizeof(float));
+    mbar_arrive_expect_tx(bars + buf, bytes);
+    float* dst = wbuf + (size_t)buf * stage_floats;
+    for (int s = 0; s < a.n_slots; ++s)
+      if (a.slot_ptr[s] != nullptr)
+        bulk_g2s(dst + RB * 4 * a.slot_chunk0[s], a.slot_ptr[s] + row0 * a.slot_ld[s],
+                 (uint32_t)(rows * a.slot_ld[s] * sizeof(float)), bars + buf, policy);
+  };
+  if constexpr (STAGED) {
+    const int wic = threadIdx.x >> 5;
+    wbuf = reinterpret_cast<float*>(sweep_smem) + (size_t)wic * NS * stage_floats;
+    bars = reinterpret_cast<uint64_t*>(sweep_smem + (size_t)wpc * NS * stage_floats * sizeof(float)) + wic * NS;
+    policy = l2_evict_first_policy();
+    // rows past the end of the data keep whatever the buffer held: make that finite
+    for (int i = lane; i < NS * stage_floats; i += 32) wbuf[i] = 0.f;
+    if (lane == 0)
+      for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+      for (int s = 0; s < NS; ++s)
+        if (gw + (long long)s * GW < ntiles) issue(gw + (long long)s * GW, s);
+  }
+
+  long long kt = 0;   // tiles this warp has consumed
+  for (long long tile = gw; tile < ntiles; tile += GW, ++kt) {
     const long long row0 = tile * RB;
     float4 x[RB][NCH];
+    const int buf = STAGED ? (int)(kt % NS) : 0;
+    if constexpr (STAGED) {
+      mbar_wait(bars + buf, (uint32_t)((kt / NS) & 1));
+      const float* sb = wbuf + (size_t)buf * stage_floats;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const long long row = row0 + r;
+      for (int r = 0; r < RB; ++r) {
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        x[r][i] = (cvalid[i] && row < a.n_rows) ? ldg_stream_f4(cptr[i] + row * cld[i])
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < NCH; ++i) {
+          x[r][i] = cvalid[i] ? *reinterpret_cast<const float4*>(sb + soff[i] + r * (int)cld[i])
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const long long row = row0 + r;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          x[r][i] = (cvalid[i] && row < a.n_rows) ? ldg_stream_f4(cptr[i] + row * cld[i])
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
     const long long myrow = row0 + myr;
@@ -239,6 +351,13 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const __grid_const
         p[r] = acc;
       }
       tot[h] = transpose_reduce<RB>(p, lane);
+    }
+    if constexpr (STAGED) {
+      // every lane's rows are in registers (the dot products above consumed them): hand the
+      // buffer back to the copy engine for the tile NS ahead
+      const long long nt = tile + (long long)NS * GW;
+      __syncwarp();
+      if (nt < ntiles && lane == 0) issue(nt, buf);
     }
 
     // nonlinearities, loss, delta: lane = row

@@ -55,6 +55,10 @@ class Engine:
     def synchronize(self):
         check(self.lib.rfb_engine_synchronize(self.handle))
 
+    def set_option(self, key, value):
+        """Sweep launch-shape knobs (see rfb_engine_set_option); affects models planned afterwards."""
+        check(self.lib.rfb_engine_set_option(self.handle, key.encode(), int(value)))
+
     @property
     def launch_count(self):
         n = C.c_int64()
