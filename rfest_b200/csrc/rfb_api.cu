@@ -239,8 +239,8 @@ typedef void (*SweepFn)(const SweepArgs);
 template <int H, int NCH, int RB>
 static SweepFn pick_variant(bool bwd, bool staged) {
   if (staged)
-    return bwd ? (SweepFn)sweep_kernel<H, NCH, RB, true, true> : (SweepFn)sweep_kernel<H, NCH, RB, false, true>;
-  return bwd ? (SweepFn)sweep_kernel<H, NCH, RB, true, false> : (SweepFn)sweep_kernel<H, NCH, RB, false, false>;
+    return bwd ? (SweepFn)sweep_staged_kernel<H, NCH, RB, true> : (SweepFn)sweep_staged_kernel<H, NCH, RB, false>;
+  return bwd ? (SweepFn)sweep_direct_kernel<H, NCH, RB, true> : (SweepFn)sweep_direct_kernel<H, NCH, RB, false>;
 }
 
 static int template_heads(int H) { return H <= 1 ? 1 : H <= 2 ? 2 : H <= 3 ? 3 : 5; }
@@ -413,7 +413,7 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
   SweepBuffers& sb = m->sb[kind];
   if (sb.grid != 0) return RFB_OK;
   int RB = 0;
-  const int warps = std::min(std::max(e->sweep_warps, 1), kSweepMaxThreads / 32);
+  const int warps = std::min(std::max(e->sweep_warps, 1), kSweepThreads / 32);
   const int threads = warps * 32;
   int staged = e->sweep_staged ? 1 : 0;
   int stages = std::max(e->sweep_stages, 1);
@@ -944,7 +944,9 @@ extern "C" int rfb_model_set_data(rfb_model* m, int kind, int n_slots, rfb_block
   m->sb[kind] = SweepBuffers();
   double mom[3] = {(double)n, 0.0, 0.0};
   if (y) {
-    CU(cudaMalloc(&ds.y, sizeof(float) * (size_t)n));
+    // padded by 8 zero floats: the staged sweep copies the responses of a tile as one 32-byte chunk
+    CU(cudaMalloc(&ds.y, sizeof(float) * ((size_t)n + 8)));
+    CU(cudaMemsetAsync(ds.y + n, 0, sizeof(float) * 8, e->stream));
     CU(cudaMemcpyAsync(ds.y, y, sizeof(float) * (size_t)n,
                        y_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
     ds.has_y = true;

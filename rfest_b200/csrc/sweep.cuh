@@ -40,35 +40,6 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// contiguous global -> shared copy by the copy engine, completion signalled on an mbarrier;
-// streamed data is marked evict-first in L2 (it is read exactly once per sweep)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
-                                         uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -150,29 +121,125 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   return v;
 }
 
-constexpr int kSweepMaxThreads = 128;
+constexpr int kSweepThreads = 128;   // 4 warps per CTA; several CTAs per SM
 
-// resident CTAs per SM the compiler must leave registers for (staged variant: more warps to
-// overlap the per-tile arithmetic; the copy ring, not the warp count, hides HBM latency)
+// resident CTAs per SM the compiler must leave registers for
 __host__ __device__ constexpr int sweep_min_blocks(int H, int NCH, bool staged) {
   return !staged ? 1 : (H * NCH <= 3 ? 3 : (H * NCH <= 6 ? 2 : 1));
 }
 
-// bytes of dynamic shared memory the staged variant needs
+// bytes of dynamic shared memory of the staged variant: per warp and stage the RB-row tile of
+// every design block, RB responses (padded to 32 B) and one mbarrier
+__host__ __device__ inline size_t sweep_stage_bytes(int RB, int ctot) {
+  return (size_t)RB * ctot * sizeof(float) + 32;
+}
 __host__ __device__ inline size_t sweep_smem_bytes(int warps, int stages, int RB, int ctot) {
-  return (size_t)warps * stages * ((size_t)RB * ctot * sizeof(float) + sizeof(uint64_t));
+  return (size_t)warps * stages * (sweep_stage_bytes(RB, ctot) + sizeof(unsigned long long));
 }
 
-// STAGED = false: rows go HBM -> registers with streaming 16-byte loads.
-// STAGED = true : every warp runs its own `n_stages`-deep ring of bulk-async copies (one
-//   contiguous RB x ld chunk per design block and tile), waits on the tile's mbarrier, pulls the
-//   rows into registers with conflict-free LDS.128 and immediately re-arms the buffer with the
-//   tile `n_stages` ahead -- the copy engine keeps the HBM pipe full while the warp computes.
-template <int H, int NCH, int RB, bool BWD, bool STAGED>
-__global__ void __launch_bounds__(kSweepMaxThreads, sweep_min_blocks(H, NCH, STAGED))
-sweep_kernel(const __grid_constant__ SweepArgs a) {
+// ---- per-row epilogue shared by both variants: nonlinearities, loss terms, delta -------------------
+// `tot[h]` = this lane's row's dot products.  Fills r, delta-scaled head derivatives dh[] and adds
+// the row's terms to the fp32 scalar partials when `count`.
+template <int H>
+__device__ __forceinline__ void row_epilogue(const SweepArgs& a, const float (&tot)[H], const float (&hic)[H],
+                                             float gic, bool poisson, float yv, bool rowok, bool count,
+                                             float (&dh)[H], float& r_out, float (&sc)[kNumScalars]) {
+  float u = 0.f;
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    float f;
+    nl_eval(a.head_nl[h], tot[h] + hic[h], f, dh[h]);
+    u += f;
+  }
+  u += gic;
+  float r, dr;
+  nl_eval(a.out_nl, u, r, dr);
+  float la, lb, dldr;
+  const float err = yv - r;
+  if (poisson) {                                   // rfest/loss.py:4-11
+    const bool fin = r != CUDART_INF_F;
+    const float r1 = fin ? r : 0.f;
+    const bool live = fin && (r1 > 1e-20f);
+    const float r2 = (r1 != r1) ? r1 : fmaxf(r1, 1e-20f);
+    la = -logf(r2) * yv;
+    lb = r2;
+    dldr = live ? (1.0f - yv / r2) : 0.f;
+  } else {                                         // rfest/loss.py:14-16
+    la = err * err;
+    lb = 0.f;
+    dldr = -err * a.two_over_n;
+  }
+  float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
+  if (count) {
+    sc[S_LOSS_A] += la;
+    sc[S_LOSS_B] += lb;
+    sc[S_R] += r;
+    sc[S_RR] += r * r;
+    sc[S_YR] += yv * r;
+    sc[S_SQERR] += err * err;
+    sc[S_GGLOBAL] += delta;
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    dh[h] = (delta == 0.f) ? 0.f : delta * dh[h];
+    if (count) sc[S_GHEAD + h] += dh[h];
+  }
+  r_out = r;
+}
+
+// fp32 partials -> this warp's fp64 accumulator row (L2 resident).  The row was zeroed at kernel
+// start, so this is always read-modify-write.  Scalars live in lanes < RB only.
+template <int H, int NCH, int RB, bool BWD>
+__device__ __forceinline__ void flush_partials(double* my_acc, int ctot, int lane, const bool (&cvalid)[NCH],
+                                               float4 (&g)[H][NCH], float (&sc)[kNumScalars]) {
+  if (BWD) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        if (cvalid[i]) {
+          double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)h * ctot + 4 * (lane + 32 * i));
+          double2 lo = p2[0], hi = p2[1];
+          lo.x += (double)g[h][i].x; lo.y += (double)g[h][i].y;
+          hi.x += (double)g[h][i].z; hi.y += (double)g[h][i].w;
+          p2[0] = lo;
+          p2[1] = hi;
+        }
+        g[h][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < S_GHEAD + H; ++k) {
+    double v = (double)sc[k];
+#pragma unroll
+    for (int m = RB / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) my_acc[(size_t)H * ctot + k] += v;
+    sc[k] = 0.f;
+  }
+}
+
+template <int H, int NCH, bool BWD>
+__device__ __forceinline__ void cta_reduce(const SweepArgs& a, int ctot, int NE) {
+  // fixed-order fp64 reduction over the CTA's warps (a forward-only sweep leaves the gradient
+  // part of its rows untouched: nobody reads it)
+  __syncthreads();
+  const int wpc = blockDim.x >> 5;
+  const double* cta_rows = a.warp_acc + (size_t)blockIdx.x * wpc * NE;
+  double* out = a.cta_part + (size_t)blockIdx.x * NE;
+  for (int e = (BWD ? 0 : H * ctot) + threadIdx.x; e < NE; e += blockDim.x) {
+    double s = 0.0;
+    for (int wv = 0; wv < wpc; ++wv) s += cta_rows[(size_t)wv * NE + e];
+    out[e] = s;
+  }
+}
+
+// ================================================================================================
+// Variant A -- direct: rows go HBM -> registers with streaming 16-byte loads.
+// ================================================================================================
+template <int H, int NCH, int RB, bool BWD>
+__global__ void __launch_bounds__(kSweepThreads) sweep_direct_kernel(const __grid_constant__ SweepArgs a) {
   static_assert(RB >= 1 && RB <= 32 && (RB & (RB - 1)) == 0, "RB must be a power of two");
-  extern __shared__ __align__(128) unsigned char sweep_smem[];
   const int lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   const long long gw = (long long)blockIdx.x * wpc + (threadIdx.x >> 5);
@@ -180,27 +247,22 @@ sweep_kernel(const __grid_constant__ SweepArgs a) {
   const int ctot = a.n_chunks * 4;
   const int NE = H * ctot + kNumScalars;
 
-  // ---- column ownership -------------------------------------------------------------
   const float* cptr[NCH];
   long long cld[NCH];
-  int soff[NCH];   // staged: float offset of this lane's chunk inside a stage buffer
   bool cvalid[NCH];
-  float4 w[H][NCH];
-  float4 g[H][NCH];
+  float4 w[H][NCH], g[H][NCH];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = lane + 32 * i;
     cvalid[i] = c < a.n_chunks;
     cptr[i] = nullptr;
     cld[i] = 0;
-    soff[i] = 0;
     if (cvalid[i]) {
       int s = 0;
       while (s + 1 < a.n_slots && c >= a.slot_chunk0[s + 1]) ++s;
       cvalid[i] = a.slot_ptr[s] != nullptr;   // slot without a block in this data set
       cptr[i] = a.slot_ptr[s] + 4 * (c - a.slot_chunk0[s]);
       cld[i] = a.slot_ld[s];
-      soff[i] = RB * 4 * a.slot_chunk0[s] + 4 * (c - a.slot_chunk0[s]);
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -214,126 +276,31 @@ sweep_kernel(const __grid_constant__ SweepArgs a) {
   for (int h = 0; h < H; ++h) hic[h] = a.head_icpt[h];
   const float gic = a.glob_icpt[0];
   const bool poisson = a.distr == RFB_DISTR_POISSON;
-
   float sc[kNumScalars];
 #pragma unroll
   for (int k = 0; k < kNumScalars; ++k) sc[k] = 0.f;
-
   double* my_acc = a.warp_acc + (size_t)gw * NE;
-  bool first_flush = true;
+  for (int e = lane; e < NE; e += 32) my_acc[e] = 0.0;
+  __syncwarp();
   int since_flush = 0;
 
-  auto flush = [&]() {
-    if (BWD) {
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          if (cvalid[i]) {
-            double* p = my_acc + (size_t)h * ctot + 4 * (lane + 32 * i);
-            double2* p2 = reinterpret_cast<double2*>(p);
-            double2 lo = make_double2((double)g[h][i].x, (double)g[h][i].y);
-            double2 hi = make_double2((double)g[h][i].z, (double)g[h][i].w);
-            if (!first_flush) {
-              const double2 olo = p2[0], ohi = p2[1];
-              lo.x += olo.x; lo.y += olo.y; hi.x += ohi.x; hi.y += ohi.y;
-            }
-            p2[0] = lo;
-            p2[1] = hi;
-          }
-          g[h][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kNumScalars; ++k) {
-      if (k < S_GHEAD + H) {
-        double v = warp_sum_f64((double)sc[k]);
-        if (lane == 0) {
-          double* p = my_acc + (size_t)H * ctot + k;
-          *p = first_flush ? v : (*p + v);
-        }
-      } else if (first_flush && lane == 0) {
-        my_acc[(size_t)H * ctot + k] = 0.0;
-      }
-      sc[k] = 0.f;
-    }
-    first_flush = false;
-    since_flush = 0;
-  };
-
-  // ---- stream the rows ------------------------------------------------------------------
   const long long ntiles = (a.n_rows + RB - 1) / RB;
   const int myr = lane & (RB - 1);
-
-  // staged: this warp's ring of stage buffers and their mbarriers
-  const int NS = a.n_stages;
-  const int stage_floats = RB * ctot;
-  float* wbuf = nullptr;
-  uint64_t* bars = nullptr;
-  uint64_t policy = 0;
-  auto issue = [&](long long tile, int buf) {   // lane 0: arm the barrier, start the copies
-    const long long row0 = tile * RB;
-    const int rows = (int)((a.n_rows - row0 < RB) ? (a.n_rows - row0) : RB);
-    uint32_t bytes = 0;
-    for (int s = 0; s < a.n_slots; ++s)
-      if (a.slot_ptr[s] != nullptr) bytes += (uint32_t)(rows * a.slot_ld[s] * sizeof(float));
-    mbar_arrive_expect_tx(bars + buf, bytes);
-    float* dst = wbuf + (size_t)buf * stage_floats;
-    for (int s = 0; s < a.n_slots; ++s)
-      if (a.slot_ptr[s] != nullptr)
-        bulk_g2s(dst + RB * 4 * a.slot_chunk0[s], a.slot_ptr[s] + row0 * a.slot_ld[s],
-                 (uint32_t)(rows * a.slot_ld[s] * sizeof(float)), bars + buf, policy);
-  };
-  if constexpr (STAGED) {
-    const int wic = threadIdx.x >> 5;
-    wbuf = reinterpret_cast<float*>(sweep_smem) + (size_t)wic * NS * stage_floats;
-    bars = reinterpret_cast<uint64_t*>(sweep_smem + (size_t)wpc * NS * stage_floats * sizeof(float)) + wic * NS;
-    policy = l2_evict_first_policy();
-    // rows past the end of the data keep whatever the buffer held: make that finite
-    for (int i = lane; i < NS * stage_floats; i += 32) wbuf[i] = 0.f;
-    if (lane == 0)
-      for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0)
-      for (int s = 0; s < NS; ++s)
-        if (gw + (long long)s * GW < ntiles) issue(gw + (long long)s * GW, s);
-  }
-
-  long long kt = 0;   // tiles this warp has consumed
-  for (long long tile = gw; tile < ntiles; tile += GW, ++kt) {
+  for (long long tile = gw; tile < ntiles; tile += GW) {
     const long long row0 = tile * RB;
     float4 x[RB][NCH];
-    const int buf = STAGED ? (int)(kt % NS) : 0;
-    if constexpr (STAGED) {
-      mbar_wait(bars + buf, (uint32_t)((kt / NS) & 1));
-      const float* sb = wbuf + (size_t)buf * stage_floats;
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
+    for (int r = 0; r < RB; ++r) {
+      const long long row = row0 + r;
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          x[r][i] = cvalid[i] ? *reinterpret_cast<const float4*>(sb + soff[i] + r * (int)cld[i])
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const long long row = row0 + r;
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          x[r][i] = (cvalid[i] && row < a.n_rows) ? ldg_stream_f4(cptr[i] + row * cld[i])
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
+      for (int i = 0; i < NCH; ++i)
+        x[r][i] = (cvalid[i] && row < a.n_rows) ? ldg_stream_f4(cptr[i] + row * cld[i])
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const long long myrow = row0 + myr;
     const bool rowok = myrow < a.n_rows;
     const float yv = (rowok && a.y != nullptr) ? __ldg(a.y + myrow) : 0.f;
 
-    // forward: per-head dot products, transposed reduction
     float tot[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -352,93 +319,270 @@ sweep_kernel(const __grid_constant__ SweepArgs a) {
       }
       tot[h] = transpose_reduce<RB>(p, lane);
     }
-    if constexpr (STAGED) {
-      // every lane's rows are in registers (the dot products above consumed them): hand the
-      // buffer back to the copy engine for the tile NS ahead
-      const long long nt = tile + (long long)NS * GW;
-      __syncwarp();
-      if (nt < ntiles && lane == 0) issue(nt, buf);
-    }
-
-    // nonlinearities, loss, delta: lane = row
-    float dh[H];
-    float u = 0.f;
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      float f;
-      nl_eval(a.head_nl[h], tot[h] + hic[h], f, dh[h]);
-      u += f;
-    }
-    u += gic;
-    float r, dr;
-    nl_eval(a.out_nl, u, r, dr);
-
-    float la, lb, dldr;
-    const float err = yv - r;
-    if (poisson) {                                   // rfest/loss.py:4-11
-      const bool fin = r != CUDART_INF_F;
-      const float r1 = fin ? r : 0.f;
-      const bool live = fin && (r1 > 1e-20f);
-      const float r2 = (r1 != r1) ? r1 : fmaxf(r1, 1e-20f);
-      la = -logf(r2) * yv;
-      lb = r2;
-      dldr = live ? (1.0f - yv / r2) : 0.f;
-    } else {                                         // rfest/loss.py:14-16
-      la = err * err;
-      lb = 0.f;
-      dldr = -err * a.two_over_n;
-    }
-    float delta = (dldr == 0.f) ? 0.f : dldr * dr;
+    float dh[H], r;
     const bool count = rowok && (lane < RB);
-    if (!rowok) delta = 0.f;
-    if (count) {
-      sc[S_LOSS_A] += la;
-      sc[S_LOSS_B] += lb;
-      sc[S_R] += r;
-      sc[S_RR] += r * r;
-      sc[S_YR] += yv * r;
-      sc[S_SQERR] += err * err;
-      sc[S_GGLOBAL] += delta;
-      sc[S_BAD] += (r != r) ? 1.f : 0.f;
-    }
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      dh[h] = (delta == 0.f) ? 0.f : delta * dh[h];
-      if (count) sc[S_GHEAD + h] += dh[h];
-    }
+    row_epilogue<H>(a, tot, hic, gic, poisson, yv, rowok, count, dh, r, sc);
     if (a.r_out != nullptr && count) a.r_out[myrow] = r;
-
-    // backward: G_h += delta_h(row) * x(row)
     if (BWD) {
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
+      for (int rr = 0; rr < RB; ++rr) {
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          const float d = __shfl_sync(0xffffffffu, dh[h], r);
+          const float d = __shfl_sync(0xffffffffu, dh[h], rr);
 #pragma unroll
           for (int i = 0; i < NCH; ++i) {
-            g[h][i].x = fmaf(d, x[r][i].x, g[h][i].x);
-            g[h][i].y = fmaf(d, x[r][i].y, g[h][i].y);
-            g[h][i].z = fmaf(d, x[r][i].z, g[h][i].z);
-            g[h][i].w = fmaf(d, x[r][i].w, g[h][i].w);
+            g[h][i].x = fmaf(d, x[rr][i].x, g[h][i].x);
+            g[h][i].y = fmaf(d, x[rr][i].y, g[h][i].y);
+            g[h][i].z = fmaf(d, x[rr][i].z, g[h][i].z);
+            g[h][i].w = fmaf(d, x[rr][i].w, g[h][i].w);
           }
         }
       }
     }
-    if (++since_flush >= a.flush_tiles) flush();
+    if (++since_flush >= a.flush_tiles) {
+      flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+      since_flush = 0;
+    }
   }
-  flush();  // every warp writes its row, even with no tiles
+  flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+  cta_reduce<H, NCH, BWD>(a, ctot, NE);
+}
 
-  // ---- fixed-order fp64 reduction over the CTA's warps ---------------------------------------
-  __syncthreads();
-  const double* cta_rows = a.warp_acc + (size_t)blockIdx.x * wpc * NE;
-  double* out = a.cta_part + (size_t)blockIdx.x * NE;
-  // (a forward-only sweep leaves the gradient part of its rows untouched: nobody reads it)
-  for (int e = (BWD ? 0 : H * ctot) + threadIdx.x; e < NE; e += blockDim.x) {
-    double s = 0.0;
-    for (int wv = 0; wv < wpc; ++wv) s += cta_rows[(size_t)wv * NE + e];
-    out[e] = s;
+// ================================================================================================
+// Variant B -- staged (default): every warp runs its own `n_stages`-deep ring of bulk-async
+// copies (cp.async.bulk: one contiguous RB x ld chunk per design block and tile, plus the RB
+// responses), waits on the tile's mbarrier, pulls the rows into registers with conflict-free
+// LDS.128 and immediately re-arms the buffer with the tile `n_stages` ahead.  The copy engine
+// keeps the HBM pipe full while the warp computes; nothing in the loop touches global memory.
+// ================================================================================================
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                           uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+template <int H, int NCH, int RB, bool BWD>
+__global__ void __launch_bounds__(kSweepThreads, sweep_min_blocks(H, NCH, true))
+sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
+  static_assert(RB >= 1 && RB <= 8 && (RB & (RB - 1)) == 0, "RB must be 1, 2, 4 or 8");
+  extern __shared__ __align__(128) unsigned char sweep_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wic = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  const long long gw = (long long)blockIdx.x * wpc + wic;
+  const long long GW = (long long)gridDim.x * wpc;
+  const int ctot = a.n_chunks * 4;
+  const int NE = H * ctot + kNumScalars;
+  const int NS = a.n_stages;
+  const uint32_t stage_bytes = (uint32_t)sweep_stage_bytes(RB, ctot);
+  const uint32_t y_off = (uint32_t)(RB * ctot * sizeof(float));       // responses sit after the rows
+
+  // ---- column ownership.  A lane's unused chunk slots alias its first chunk with zero weights,
+  // so the inner loops carry no predicates (the loaded values are finite data, times zero).
+  uint32_t laddr[NCH], lstride[NCH];
+  bool cvalid[NCH];
+  float4 w[H][NCH], g[H][NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    cvalid[i] = c < a.n_chunks;
+    laddr[i] = 0;
+    lstride[i] = 0;
+    if (cvalid[i]) {
+      int s = 0;
+      while (s + 1 < a.n_slots && c >= a.slot_chunk0[s + 1]) ++s;
+      cvalid[i] = a.slot_ptr[s] != nullptr;
+      laddr[i] = (uint32_t)((RB * 4 * a.slot_chunk0[s] + 4 * (c - a.slot_chunk0[s])) * sizeof(float));
+      lstride[i] = (uint32_t)(a.slot_ld[s] * sizeof(float));
+    }
+    if (!cvalid[i]) {
+      laddr[i] = laddr[0];
+      lstride[i] = lstride[0];
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      w[h][i] = cvalid[i] ? *reinterpret_cast<const float4*>(a.W + (size_t)h * ctot + 4 * c)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[h][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
+  float hic[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) hic[h] = a.head_icpt[h];
+  const float gic = a.glob_icpt[0];
+  const bool poisson = a.distr == RFB_DISTR_POISSON;
+  float sc[kNumScalars];
+#pragma unroll
+  for (int k = 0; k < kNumScalars; ++k) sc[k] = 0.f;
+  double* my_acc = a.warp_acc + (size_t)gw * NE;
+  for (int e = lane; e < NE; e += 32) my_acc[e] = 0.0;
+
+  // ---- the copies: lane s moves design block s, lane n_slots moves the responses ------------------
+  const char* my_src = nullptr;
+  uint32_t my_rowbytes = 0, my_dst = 0, all_rowbytes = 0;
+  for (int s = 0; s < a.n_slots; ++s) {
+    if (a.slot_ptr[s] == nullptr) continue;
+    all_rowbytes += (uint32_t)(a.slot_ld[s] * sizeof(float));
+    if (lane == s) {
+      my_src = reinterpret_cast<const char*>(a.slot_ptr[s]);
+      my_rowbytes = (uint32_t)(a.slot_ld[s] * sizeof(float));
+      my_dst = (uint32_t)(RB * 4 * a.slot_chunk0[s] * sizeof(float));
+    }
+  }
+  constexpr bool kStageY = RB >= 4;   // a 32-byte bulk copy needs a 16-byte aligned source
+  const bool has_y = a.y != nullptr;
+  if (kStageY && has_y && lane == a.n_slots) {
+    my_src = reinterpret_cast<const char*>(a.y);
+    my_rowbytes = sizeof(float);
+    my_dst = y_off;
+  }
+  const bool y_lane = kStageY && has_y && lane == a.n_slots;
+  const uint32_t tile_y_bytes = (kStageY && has_y) ? 32u : 0u;   // RB <= 8 responses as 32 B (y is padded)
+
+  const uint32_t wbase = smem_u32(sweep_smem) + (uint32_t)wic * NS * stage_bytes;
+  const uint32_t bbase = smem_u32(sweep_smem) + (uint32_t)wpc * NS * stage_bytes + (uint32_t)wic * NS * 8u;
+  const uint64_t policy = l2_evict_first_policy();
+  const long long ntiles = (a.n_rows + RB - 1) / RB;
+
+  auto issue = [&](long long tile, uint32_t stage_addr, uint32_t bar) {
+    const long long row0 = tile * RB;
+    const long long left = a.n_rows - row0;
+    const uint32_t rows = left < RB ? (uint32_t)left : (uint32_t)RB;
+    if (lane == 0) mbar_arrive_expect_tx_a(bar, rows * all_rowbytes + tile_y_bytes);
+    if (my_rowbytes != 0) {
+      const uint32_t bytes = y_lane ? 32u : rows * my_rowbytes;
+      bulk_g2s_a(stage_addr + my_dst, my_src + row0 * my_rowbytes, bytes, bar, policy);
+    }
+  };
+
+  // rows past the end of the data keep whatever the buffer held: make that finite
+  for (uint32_t o = lane * 4u; o < (uint32_t)NS * stage_bytes; o += 128u)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(wbase + o), "r"(0u) : "memory");
+  if (lane == 0)
+    for (int s = 0; s < NS; ++s) mbar_init_a(bbase + 8u * s, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  for (int s = 0; s < NS; ++s)
+    if (gw + (long long)s * GW < ntiles) issue(gw + (long long)s * GW, wbase + s * stage_bytes, bbase + 8u * s);
+
+  const int myr = lane & (RB - 1);
+  int since_flush = 0;
+  int buf = 0;
+  uint32_t phase = 0;
+  for (long long tile = gw; tile < ntiles; tile += GW) {
+    const uint32_t stage_addr = wbase + (uint32_t)buf * stage_bytes;
+    const uint32_t bar = bbase + 8u * (uint32_t)buf;
+    mbar_wait_a(bar, phase);
+
+    float4 x[RB][NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      uint32_t ad = stage_addr + laddr[i];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        x[r][i] = lds_f4(ad);
+        ad += lstride[i];
+      }
+    }
+    float yv = 0.f;
+    if (has_y) {
+      if (kStageY) yv = lds_f1(stage_addr + y_off + 4u * (uint32_t)myr);
+      else if (tile * RB + myr < a.n_rows) yv = __ldg(a.y + tile * RB + myr);
+    }
+
+    float tot[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float p[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          acc = fmaf(x[r][i].x, w[h][i].x, acc);
+          acc = fmaf(x[r][i].y, w[h][i].y, acc);
+          acc = fmaf(x[r][i].z, w[h][i].z, acc);
+          acc = fmaf(x[r][i].w, w[h][i].w, acc);
+        }
+        p[r] = acc;
+      }
+      tot[h] = transpose_reduce<RB>(p, lane);
+    }
+    // every lane's rows (and y) are in registers -- the dot products consumed them: hand the
+    // buffer back to the copy engine for the tile NS ahead
+    {
+      const long long nt = tile + (long long)NS * GW;
+      __syncwarp();
+      if (nt < ntiles) issue(nt, stage_addr, bar);
+    }
+
+    const long long myrow = tile * RB + myr;
+    const bool rowok = myrow < a.n_rows;
+    const bool count = rowok && (lane < RB);
+    float dh[H], r;
+    row_epilogue<H>(a, tot, hic, gic, poisson, rowok ? yv : 0.f, rowok, count, dh, r, sc);
+    if (a.r_out != nullptr && count) a.r_out[myrow] = r;
+    if (BWD) {
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float d = __shfl_sync(0xffffffffu, dh[h], rr);
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            g[h][i].x = fmaf(d, x[rr][i].x, g[h][i].x);
+            g[h][i].y = fmaf(d, x[rr][i].y, g[h][i].y);
+            g[h][i].z = fmaf(d, x[rr][i].z, g[h][i].z);
+            g[h][i].w = fmaf(d, x[rr][i].w, g[h][i].w);
+          }
+        }
+      }
+    }
+    if (++buf == NS) {
+      buf = 0;
+      phase ^= 1u;
+    }
+    if (++since_flush >= a.flush_tiles) {
+      flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+      since_flush = 0;
+    }
+  }
+  flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+  cta_reduce<H, NCH, BWD>(a, ctot, NE);
 }
 
 // out[e] = sum_p part[p][e]: thread x = entry, thread y = strided slice of the partials.
