@@ -110,9 +110,9 @@ struct rfb_engine {
   Scratch stage, zbuf, stbuf, sxybuf, small;
   // sweep launch shape (tunable: rfb_engine_set_option / RFB_SWEEP_* environment variables)
   int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
-  int sweep_stages = 3;   // depth of each warp's copy ring
+  int sweep_stages = 2;   // depth of each warp's copy ring
   int sweep_warps = 4;    // warps per CTA
-  int sweep_ctas = 0;     // CTAs per SM (0: as many as fit)
+  int sweep_ctas = 2;     // CTAs per SM (0: as many as fit); 2 x 4 warps measured best on B200
 };
 
 static int scratch_reserve(rfb_engine* e, Scratch& s, size_t bytes) {

@@ -121,11 +121,11 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   return v;
 }
 
-constexpr int kSweepThreads = 128;   // 4 warps per CTA; several CTAs per SM
+constexpr int kSweepThreads = 192;   // at most 6 warps per CTA (default 4); several CTAs per SM
 
 // resident CTAs per SM the compiler must leave registers for
 __host__ __device__ constexpr int sweep_min_blocks(int H, int NCH, bool staged) {
-  return !staged ? 1 : (H * NCH <= 3 ? 3 : (H * NCH <= 6 ? 2 : 1));
+  return !staged ? 1 : (H * NCH <= 3 ? 2 : 1);   // x 192 threads: <= 170 registers for the narrow shapes
 }
 
 // bytes of dynamic shared memory of the staged variant: per warp and stage the RB-row tile of

@@ -31,12 +31,15 @@ m.alpha, m.beta = 1.0, 0.01
 m.y["train"] = y[24:].cpu().numpy()
 n = n_raw - 24
 bytes_ = 4.0 * n * 297
-configs = [(0, 1, 0)] + [(1, s, c) for s, c in itertools.product((2, 3, 4), (1, 2, 3))]
+configs = [(0, 1, 0, 4)] + [(1, s, c, w) for s, c, w in
+                             [(2, 2, 4), (2, 2, 5), (2, 2, 6), (2, 3, 3), (2, 3, 4), (3, 2, 4), (3, 2, 3),
+                              (2, 1, 6), (3, 1, 6), (2, 4, 2), (2, 4, 3), (2, 5, 2)]]
 ref = None
-for staged, stages, ctas in configs:
+for staged, stages, ctas, warps in configs:
     eng.set_option("sweep_staged", staged)
     eng.set_option("sweep_stages", stages)
     eng.set_option("sweep_ctas", ctas)
+    eng.set_option("sweep_warps", warps)
     m._dirty = True
     m._sync()
     dm = m._dm
@@ -50,6 +53,6 @@ for staged, stages, ctas in configs:
     if ref is None:
         ref = tr
     dev = float(np.max(np.abs(tr - ref) / np.abs(ref)))
-    print(f"staged={staged} stages={stages} ctas/SM={ctas or 'max'}: sweep {ms[0]:.3f} ms  "
+    print(f"staged={staged} stages={stages} ctas/SM={ctas or 'max'} warps/CTA={warps}: sweep {ms[0]:.3f} ms  "
           f"{bytes_ / ms[0] / 1e6:.0f} GB/s  ({bytes_ / ms[0] / 1e6 / 6551:.3f} of measured)  "
           f"loss dev vs first {dev:.1e}", flush=True)
