@@ -236,22 +236,32 @@ struct rfb_model {
 // ------------------------------------------------------------------------------------------------
 typedef void (*SweepFn)(const SweepArgs);
 
+template <int H, int NCH, int RB, int SPEC>
+static SweepFn pick_staged(bool bwd) {
+  return bwd ? (SweepFn)sweep_staged_kernel<H, NCH, RB, true, SPEC> : (SweepFn)sweep_staged_kernel<H, NCH, RB, false, SPEC>;
+}
+
 template <int H, int NCH, int RB>
-static SweepFn pick_variant(bool bwd, bool staged) {
-  if (staged)
-    return bwd ? (SweepFn)sweep_staged_kernel<H, NCH, RB, true> : (SweepFn)sweep_staged_kernel<H, NCH, RB, false>;
-  return bwd ? (SweepFn)sweep_direct_kernel<H, NCH, RB, true> : (SweepFn)sweep_direct_kernel<H, NCH, RB, false>;
+static SweepFn pick_variant(bool bwd, bool staged, int spec) {
+  if (!staged)
+    return bwd ? (SweepFn)sweep_direct_kernel<H, NCH, RB, true> : (SweepFn)sweep_direct_kernel<H, NCH, RB, false>;
+  if constexpr (H == 1) {   // the compile-time model specialisations exist for single-head models
+    if (spec == 1) return pick_staged<H, NCH, RB, 1>(bwd);
+    if (spec == 2) return pick_staged<H, NCH, RB, 2>(bwd);
+    if (spec == 3) return pick_staged<H, NCH, RB, 3>(bwd);
+  }
+  return pick_staged<H, NCH, RB, 0>(bwd);
 }
 
 static int template_heads(int H) { return H <= 1 ? 1 : H <= 2 ? 2 : H <= 3 ? 3 : 5; }
 static int template_chunks(int nch) { return nch <= 1 ? 1 : nch <= 3 ? 3 : nch <= 5 ? 5 : 10; }
 
 // rows per tile for each (heads, chunks-per-lane) instance: bounded by registers
-static SweepFn sweep_instance(int Ht, int NCH, bool bwd, bool staged, int* RB) {
-#define INST(h, c, rb)                          \
-  if (Ht == h && NCH == c) {                    \
-    *RB = rb;                                   \
-    return pick_variant<h, c, rb>(bwd, staged); \
+static SweepFn sweep_instance(int Ht, int NCH, bool bwd, bool staged, int spec, int* RB) {
+#define INST(h, c, rb)                                \
+  if (Ht == h && NCH == c) {                          \
+    *RB = rb;                                         \
+    return pick_variant<h, c, rb>(bwd, staged, spec); \
   }
   INST(1, 1, 8) INST(1, 3, 8) INST(1, 5, 4) INST(1, 10, 2)
   INST(2, 1, 8) INST(2, 3, 8) INST(2, 5, 4) INST(2, 10, 1)
@@ -305,7 +315,7 @@ static int build_plan(rfb_model* m) {
   if (nch > 10)
     return fail(RFB_ERR_UNSUPPORTED, "%d design columns per sample (max 1280)", p.ctot);
   p.NCH = template_chunks(nch);
-  if (!sweep_instance(p.Ht, p.NCH, true, false, &p.RB)) {
+  if (!sweep_instance(p.Ht, p.NCH, true, false, 0, &p.RB)) {
     // fall back to a larger head template that exists for this width
     return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel for %d heads x %d columns", p.H, p.ctot);
   }
@@ -404,6 +414,18 @@ static void invalidate_plan(rfb_model* m) {
   m->plan.ok = false;
 }
 
+// compile-time model specialisation of the staged sweep (see row_epilogue), 0 = none
+static int sweep_spec(const rfb_model* m, const int* head_nl) {
+  const Plan& p = m->plan;
+  if (p.Ht != 1) return 0;
+  for (int h = 0; h < p.Ht; ++h)
+    if (head_nl[h] != RFB_NL_NONE) return 0;
+  if (m->distr == RFB_DISTR_POISSON && m->out_nl == RFB_NL_SOFTPLUS) return 1;
+  if (m->distr == RFB_DISTR_POISSON && m->out_nl == RFB_NL_EXPONENTIAL) return 2;
+  if (m->distr == RFB_DISTR_GAUSSIAN && m->out_nl == RFB_NL_NONE) return 3;
+  return 0;
+}
+
 // Size the launch and allocate the scratch of the sweeps over data set `kind` (not capturable,
 // so it happens before any graph capture).
 static int ensure_sweep_buffers(rfb_model* m, int kind) {
@@ -424,7 +446,8 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
     occ = 0;
     bool ok = true;
     for (int bwd = 0; bwd < 2 && ok; ++bwd) {
-      SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd != 0, staged != 0, &RB);
+      for (int spec = 0; spec < kNumSpecs && ok; ++spec) {
+      SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd != 0, staged != 0, spec, &RB);
       if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
       if (smem > 48 * 1024) {
         cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -436,7 +459,8 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
       }
       int o = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, threads, smem));
-      if (bwd) occ = o;   // the gradient sweep decides the launch shape
+      if (bwd) occ = (spec == 0) ? o : std::min(occ, o);   // the gradient sweeps decide the launch shape
+      }
     }
     if (ok && occ >= 1) break;
     if (staged && stages > 2) { --stages; continue; }       // shallower ring
@@ -470,7 +494,7 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   int RB = 0;
   TRY(ensure_sweep_buffers(m, kind));
   SweepBuffers& sb = m->sb[kind];
-  SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, &RB);
+  SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, sweep_spec(m, head_nl), &RB);
   if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
 
   SweepArgs a{};
