@@ -21,6 +21,7 @@
 #ifndef RFEST_B200_H
 #define RFEST_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -92,6 +93,10 @@ int rfb_engine_launch_count(rfb_engine* e, int64_t* out);
 int rfb_engine_set_option(rfb_engine* e, const char* key, int value);
 /* the engine's CUDA stream (cudaStream_t as an integer), for event timing by the caller */
 int rfb_engine_stream(rfb_engine* e, uint64_t* out);
+
+/* Page-locked host memory for results the caller reads back at DMA speed (predictions). */
+int rfb_host_alloc(size_t bytes, void** out);
+int rfb_host_free(void* p);
 
 /* Multi-GPU: time samples are sharded across ranks; every fit
  * iteration ends with one all-reduce of the gradient + loss/metric sums.  NCCL is

@@ -41,6 +41,8 @@ SIGNATURES = {
     "rfb_engine_launch_count": (_i, [_p, C.POINTER(_i64)]),
     "rfb_engine_set_option": (_i, [_p, C.c_char_p, _i]),
     "rfb_engine_stream": (_i, [_p, C.POINTER(_u64)]),
+    "rfb_host_alloc": (_i, [C.c_size_t, C.POINTER(_p)]),
+    "rfb_host_free": (_i, [_p]),
     "rfb_comm_unique_id": (_i, [_p]),
     "rfb_engine_comm_init": (_i, [_p, _p, _i, _i]),
     "rfb_engine_comm_info": (_i, [_p, _ip, _ip]),

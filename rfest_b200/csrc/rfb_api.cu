@@ -110,9 +110,9 @@ struct rfb_engine {
   Scratch stage, zbuf, stbuf, sxybuf, small;
   // sweep launch shape (tunable: rfb_engine_set_option / RFB_SWEEP_* environment variables)
   int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
-  int sweep_stages = 2;   // depth of each warp's copy ring
+  int sweep_stages = 0;   // depth of each warp's copy ring (0: sized for ~112 KB in flight per SM)
   int sweep_warps = 4;    // warps per CTA
-  int sweep_ctas = 2;     // CTAs per SM (0: as many as fit); 2 x 4 warps measured best on B200
+  int sweep_ctas = 1;     // CTAs per SM (0: as many as fit); 1 x 4 warps x 3 stages measured best on B200
 };
 
 static int scratch_reserve(rfb_engine* e, Scratch& s, size_t bytes) {
@@ -438,7 +438,15 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
   const int warps = std::min(std::max(e->sweep_warps, 1), kSweepThreads / 32);
   const int threads = warps * 32;
   int staged = e->sweep_staged ? 1 : 0;
-  int stages = std::max(e->sweep_stages, 1);
+  int stages = e->sweep_stages;
+  if (stages <= 0) {
+    // Measured on B200 (tools/tune_sweep.py, 2^25 x 296): bandwidth peaks with ~112 KB of rows in
+    // flight per SM (4 warps x 3 stages x 9.5 KB); both fewer and more bytes in flight are slower.
+    const int ctas = e->sweep_ctas > 0 ? e->sweep_ctas : 1;
+    const double per_stage = (double)warps * ctas * sweep_stage_bytes(p.RB, p.ctot);
+    stages = (int)std::lround(114688.0 / per_stage);
+    stages = std::min(std::max(stages, 2), 8);
+  }
   int occ = 0;
   size_t smem = 0;
   for (;;) {
@@ -613,6 +621,17 @@ extern "C" int rfb_engine_launch_count(rfb_engine* e, int64_t* out) {
 extern "C" int rfb_engine_stream(rfb_engine* e, uint64_t* out) {
   if (!e || !out) return fail(RFB_ERR_INVALID, "NULL argument");
   *out = (uint64_t)(uintptr_t)e->stream;
+  return RFB_OK;
+}
+
+extern "C" int rfb_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(RFB_ERR_INVALID, "out is NULL");
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return RFB_OK;
+}
+
+extern "C" int rfb_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
   return RFB_OK;
 }
 

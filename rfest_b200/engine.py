@@ -30,6 +30,29 @@ def as_f32(x):
     return a.ctypes.data_as(C.c_void_p), 0, a, a.shape
 
 
+class PinnedArray(np.ndarray):
+    """ndarray over page-locked host memory owned by the engine library (freed with the array)."""
+
+    _holder = None
+
+
+def pinned_empty(n, dtype=np.float32):
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    ptr = C.c_void_p()
+    check(lib.rfb_host_alloc(int(n) * dtype.itemsize, C.byref(ptr)))
+    buf = (C.c_char * (int(n) * dtype.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n)).view(PinnedArray)
+
+    class _Holder:
+        pass
+
+    holder = _Holder()
+    weakref.finalize(holder, lib.rfb_host_free, ptr)
+    arr._holder = (holder, buf)
+    return arr
+
+
 class Engine:
     """One CUDA device + stream (+ NCCL communicator).  Use `Engine.get()`."""
 
@@ -266,7 +289,7 @@ class DeviceModel:
         return b, ic
 
     def fit_predictions(self, kind, n):
-        r = np.empty(n, dtype=np.float32)
+        r = pinned_empty(n, np.float32)
         check(self.lib.rfb_fit_predictions(self.handle, _lib.KIND[kind], r.ctypes.data_as(C.c_void_p)))
         return r
 

@@ -390,12 +390,12 @@ class GLM:
         if self.engine.world > 1 and kind in self._row_range:
             lo, hi = self._row_range[kind]
             if len(y) - self.burn_in == self._n_trim[kind]:
-                return y[self.burn_in:][lo:hi].astype(np.float32)
+                return y[self.burn_in:][lo:hi].astype(np.float32, copy=False)
             if len(y) == hi - lo:
-                return y.astype(np.float32)
+                return y.astype(np.float32, copy=False)
             raise ValueError(f"`y` for `{kind}` has {len(y)} samples; expected the whole recording "
                              f"({self._n_trim[kind] + self.burn_in}) or this rank's rows ({hi - lo})")
-        return y[self.burn_in:].astype(np.float32)
+        return y[self.burn_in:].astype(np.float32, copy=False)    # a view when y is float32 already
 
     def _sync(self):
         """(Re)describe filters and data to the device model when something changed."""

@@ -31,7 +31,9 @@ m.alpha, m.beta = 1.0, 0.01
 m.y["train"] = y[24:].cpu().numpy()
 n = n_raw - 24
 bytes_ = 4.0 * n * 297
-configs = [(0, 1, 0, 4), (1, 2, 2, 4), (1, 3, 2, 4), (1, 2, 4, 2), (1, 2, 3, 3), (1, 2, 2, 3), (1, 2, 1, 4)]
+configs = [(1, st, c, w) for st, c, w in
+           [(2, 1, 4), (3, 1, 4), (4, 1, 4), (2, 1, 3), (3, 1, 3), (4, 1, 3), (2, 1, 2), (4, 1, 2), (6, 1, 2),
+            (2, 2, 2), (3, 2, 2), (4, 2, 2), (2, 2, 3), (3, 2, 3), (2, 2, 4), (2, 3, 2), (3, 3, 2)]]
 ref = None
 for staged, stages, ctas, warps in configs:
     eng.set_option("sweep_staged", staged)
