@@ -197,6 +197,9 @@ int rfb_fit_params_at(rfb_model* m, int i, float* b, double* intercepts);
 int rfb_fit_params_all(rfb_model* m, int n, float* b_all, double* icpt_all);
 /* Predictions of the final forward pass of rfb_fit_finish (y_pred['opt'][kind]). */
 int rfb_fit_predictions(rfb_model* m, int kind, float* r_out);
+/* The same predictions without leaving the device: pointer to n floats (padded to a multiple of 4),
+ * valid until the next forward pass over that data set. */
+int rfb_fit_predictions_ptr(rfb_model* m, int kind, uint64_t* dptr, int64_t* n);
 /* Release graph / traces. */
 int rfb_fit_end(rfb_model* m);
 

@@ -1103,7 +1103,7 @@ extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const doub
 
   float* d_r = nullptr;
   if (r_out) {
-    if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * (size_t)ds.n));
+    if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * ((size_t)ds.n + 4)));
     d_r = ds.r_buf;
   }
   TRY(launch_sweep(m, kind, m->tmp, head_nl.data(), false, d_r));
@@ -1359,8 +1359,8 @@ extern "C" int rfb_fit_finish(rfb_model* m, int i_last) {
   CU(cudaMemcpyAsync(f.it, &it, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   DataSet& tr = m->data[RFB_KIND_TRAIN];
   DataSet& dev = m->data[RFB_KIND_DEV];
-  if (!tr.r_buf) CU(cudaMalloc(&tr.r_buf, sizeof(float) * (size_t)tr.n));
-  if (f.has_dev && !dev.r_buf) CU(cudaMalloc(&dev.r_buf, sizeof(float) * (size_t)dev.n));
+  if (!tr.r_buf) CU(cudaMalloc(&tr.r_buf, sizeof(float) * ((size_t)tr.n + 4)));
+  if (f.has_dev && !dev.r_buf) CU(cudaMalloc(&dev.r_buf, sizeof(float) * ((size_t)dev.n + 4)));
   TRY(enqueue_iteration(m, true, tr.r_buf, f.has_dev ? dev.r_buf : nullptr));
   CU(cudaStreamSynchronize(e->stream));
   f.finished = true;
@@ -1427,6 +1427,18 @@ extern "C" int rfb_fit_predictions(rfb_model* m, int kind, float* r_out) {
   TRY(use_device(m->e));
   CU(cudaMemcpyAsync(r_out, ds.r_buf, sizeof(float) * (size_t)ds.n, cudaMemcpyDeviceToHost, m->e->stream));
   CU(cudaStreamSynchronize(m->e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_predictions_ptr(rfb_model* m, int kind, uint64_t* dptr, int64_t* n) {
+  if (!m || !dptr || !n) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind != RFB_KIND_TRAIN && kind != RFB_KIND_DEV) return fail(RFB_ERR_INVALID, "bad kind");
+  Fit& f = m->fit;
+  if (!f.active || !f.finished) return fail(RFB_ERR_STATE, "rfb_fit_finish has not been called");
+  DataSet& ds = m->data[kind];
+  if (!ds.r_buf) return fail(RFB_ERR_STATE, "no predictions for kind %d", kind);
+  *dptr = (uint64_t)(uintptr_t)ds.r_buf;
+  *n = ds.n;
   return RFB_OK;
 }
 

@@ -202,6 +202,42 @@ class Block:
         return np.asarray(self) @ np.asarray(other)
 
 
+class DeviceVector:
+    """A float32 vector resident in HBM -- what `y_pred['opt'][kind]` holds after a fit (the
+    reference keeps JAX device arrays there).  Behaves like an array where the GLM API needs it:
+    `shape`, `len()`, indexing and `np.asarray()` copy it back (once), `as_torch()` is zero-copy."""
+
+    def __init__(self, engine, device_ptr, n):
+        self.n = int(n)
+        self.shape = (self.n,)
+        self.dtype = np.dtype(np.float32)
+        self._block = Block(engine, (self.n + 3) // 4, 4)        # contiguous n floats (+ padding)
+        check(engine.lib.rfb_block_write(self._block.handle, 0, (self.n + 3) // 4,
+                                         C.c_void_p(int(device_ptr)), 1))
+        self._host = None
+
+    def __len__(self):
+        return self.n
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            self._host = self._block.read().reshape(-1)[: self.n]
+        return self._host if dtype is None else self._host.astype(dtype)
+
+    def __getitem__(self, idx):
+        return np.asarray(self)[idx]
+
+    def as_torch(self):
+        return self._block.as_torch().reshape(-1)[: self.n]
+
+    # arithmetic falls back to the host copy
+    def __sub__(self, other):
+        return np.asarray(self) - np.asarray(other)
+
+    def __rsub__(self, other):
+        return np.asarray(other) - np.asarray(self)
+
+
 class DeviceModel:
     """rfb_model handle: filters, bound data, parameters, the fit loop."""
 
@@ -289,9 +325,15 @@ class DeviceModel:
         return b, ic
 
     def fit_predictions(self, kind, n):
-        r = pinned_empty(n, np.float32)
+        r = np.empty(n, dtype=np.float32)
         check(self.lib.rfb_fit_predictions(self.handle, _lib.KIND[kind], r.ctypes.data_as(C.c_void_p)))
         return r
+
+    def fit_predictions_device(self, kind):
+        """Predictions of the final forward pass as a DeviceVector (no host copy until asked)."""
+        ptr, n = C.c_uint64(), C.c_int64()
+        check(self.lib.rfb_fit_predictions_ptr(self.handle, _lib.KIND[kind], C.byref(ptr), C.byref(n)))
+        return DeviceVector(self.engine, ptr.value, n.value)
 
     def fit_end(self):
         check(self.lib.rfb_fit_end(self.handle))

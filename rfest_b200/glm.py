@@ -634,9 +634,10 @@ class GLM:
         self.metric_dev_opt = metric_dev[best]
         self.total_time_elapsed = total_time_elapsed
         self.all_params = params_list
-        self.y_pred["opt"]["train"] = dm.fit_predictions("train", self._n_rows["train"])
+        # like the reference's JAX arrays the predictions stay on the device until they are read
+        self.y_pred["opt"]["train"] = dm.fit_predictions_device("train")
         if has_dev:
-            self.y_pred["opt"]["dev"] = dm.fit_predictions("dev", self._n_rows["dev"])
+            self.y_pred["opt"]["dev"] = dm.fit_predictions_device("dev")
         dm.fit_end()
         params = params_list[best]
         dm.set_params(*self._flatten(params))

@@ -1,0 +1,45 @@
+"""cProfile of GLM.fit through the public API at 2^log2n samples (host-side overhead hunt)."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rfest_b200 import GLM
+from rfest_b200.engine import Engine
+from rfest_b200.synth import GaussianStimulus, TensorRows, poisson_response
+
+log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 25
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+n_raw = 1 << log2n
+DIMS, DF = [25, 20, 15], [8, 6, 6]
+eng = Engine.get(0)
+stim = GaussianStimulus(n_raw, DIMS[1:], device=0)
+y = poisson_response(eng, stim, DIMS, 0, n_raw)
+m = GLM(distr="poisson", output_nonlinearity="softplus", device=0)
+m.add_design_matrix(stim, dims=DIMS, df=DF, smooth="cr", name="stimulus")
+m.add_design_matrix(TensorRows(y, 0, n_raw), dims=[20], df=[8], smooth="cr", shift=1, name="history")
+m.initialize(method="random", random_seed=2046)
+for i, name in enumerate(m.filter_names):
+    m.p0[name] = (0.1 * np.random.default_rng(2046 + i).standard_normal(m.p0[name].shape)).astype(np.float32)
+yh = torch.empty(n_raw, dtype=torch.float32).pin_memory()
+yh.copy_(y)
+yh = yh.numpy()
+kw = dict(step_size=0.01, beta=0.01, alpha=1.0, verbose=0, tolerance=0)
+m.fit(y=yh, num_iters=3, **kw)
+eng.synchronize()
+for rep in range(2):
+    t0 = time.perf_counter()
+    m.fit(y=yh, num_iters=K, **kw)
+    eng.synchronize()
+    print(f"fit({K}) wall {1e3 * (time.perf_counter() - t0):.1f} ms")
+pr = cProfile.Profile()
+pr.enable()
+m.fit(y=yh, num_iters=K, **kw)
+eng.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
