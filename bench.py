@@ -204,10 +204,10 @@ def gpu_arm(args):
     dm.fit_begin(np.full(total, STEP_SIZE), ALPHA, BETA, "corrcoef")
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device(f"cuda:{local_rank}"))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None   # samples warm-up + timed region
     dm.fit_run(W)
     eng.synchronize()
     launches0 = eng.launch_count
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
     barrier()
     eng.synchronize()
     ev0.record(ext)
