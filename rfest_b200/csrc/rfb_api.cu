@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "project.cuh"
+#include "project_tc.cuh"
 #include "sweep.cuh"
 #include "update.cuh"
 
@@ -107,7 +108,8 @@ struct rfb_engine {
   int64_t launches = 0;
   void* comm = nullptr;
   int rank = 0, world = 1;
-  Scratch stage, zbuf, stbuf, sxybuf, small;
+  Scratch stage, zbuf, stbuf, sxybuf, small, bsplit;
+  int project_tc = 1;     // spatial projection on tensor cores (tcgen05, 3xTF32) when the shape allows
   // sweep launch shape (tunable: rfb_engine_set_option / RFB_SWEEP_* environment variables)
   int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
   int sweep_stages = 0;   // depth of each warp's copy ring (0: sized for ~112 KB in flight per SM)
@@ -579,6 +581,7 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   if (const char* v = getenv("RFB_SWEEP_STAGES")) e->sweep_stages = atoi(v);
   if (const char* v = getenv("RFB_SWEEP_WARPS")) e->sweep_warps = atoi(v);
   if (const char* v = getenv("RFB_SWEEP_CTAS")) e->sweep_ctas = atoi(v);
+  if (const char* v = getenv("RFB_PROJECT_TC")) e->project_tc = atoi(v);
   *out = e;
   return RFB_OK;
 }
@@ -590,6 +593,7 @@ extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) 
   else if (k == "sweep_stages") e->sweep_stages = value;
   else if (k == "sweep_warps") e->sweep_warps = value;
   else if (k == "sweep_ctas") e->sweep_ctas = value;
+  else if (k == "project_tc") e->project_tc = value;
   else return fail(RFB_ERR_INVALID, "unknown option '%s'", key);
   return RFB_OK;
 }
@@ -599,7 +603,7 @@ extern "C" int rfb_engine_destroy(rfb_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-  for (Scratch* s : {&e->stage, &e->zbuf, &e->stbuf, &e->sxybuf, &e->small}) cudaFree(s->p);
+  for (Scratch* s : {&e->stage, &e->zbuf, &e->stbuf, &e->sxybuf, &e->small, &e->bsplit}) cudaFree(s->p);
   cudaStreamDestroy(e->stream);
   delete e;
   return RFB_OK;
@@ -759,6 +763,116 @@ extern "C" int rfb_block_write(rfb_block* b, int64_t row0, int64_t n, const floa
   return RFB_OK;
 }
 
+// ---- tensor-core spatial projection (project_tc.cuh) ---------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// fp32 row-major [rows x cols] (row pitch `pitch_floats`), box = 32 columns x `box_rows` rows, 128-byte swizzle
+static bool make_map_2d(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t pitch_floats,
+                        uint32_t box_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch_floats * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kTcK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct TcPlan {
+  bool ok = false;
+  int n_pad = 0, k_tiles = 0, stages = 0, tmem_cols = 0;
+  size_t smem = 0;
+  const float *bhi = nullptr, *blo = nullptr;   // device, [n_pad x k_tiles*32], K contiguous
+  CUtensorMap map_bhi, map_blo;
+};
+
+// Decide whether Z = stim @ Sxy can run on the tensor cores and stage the split, transposed B.
+static int tc_prepare(rfb_engine* e, const float* Sxy, int n_pix, int n_q, TcPlan* tp) {
+  tp->ok = false;
+  if (!e->project_tc || !Sxy) return RFB_OK;
+  if (n_pix < 64 || (n_pix % 4) != 0 || n_q < 8 || n_q > 128) return RFB_OK;
+  if (!tensor_map_encoder()) return RFB_OK;
+  tp->n_pad = (n_q + 15) / 16 * 16;
+  tp->k_tiles = (n_pix + kTcK - 1) / kTcK;
+  const int kpad = tp->k_tiles * kTcK;
+  tp->tmem_cols = 32;
+  while (tp->tmem_cols < 2 * tp->n_pad) tp->tmem_cols *= 2;
+  tp->stages = (int)std::min<size_t>(6, (200 * 1024) / tc_stage_bytes(tp->n_pad));
+  if (tp->stages < 2) return RFB_OK;
+  tp->smem = tc_smem_bytes(tp->n_pad, tp->stages);
+  // hi = tf32 truncation of b, lo = b - hi (exact); transposed so that K is contiguous (K-major B)
+  std::vector<float> h((size_t)2 * tp->n_pad * kpad, 0.f);
+  float* hi = h.data();
+  float* lo = h.data() + (size_t)tp->n_pad * kpad;
+  for (int k = 0; k < n_pix; ++k)
+    for (int q = 0; q < n_q; ++q) {
+      const float b = Sxy[(size_t)k * n_q + q];
+      uint32_t u;
+      memcpy(&u, &b, 4);
+      u &= 0xFFFFE000u;
+      float bh;
+      memcpy(&bh, &u, 4);
+      hi[(size_t)q * kpad + k] = bh;
+      lo[(size_t)q * kpad + k] = b - bh;
+    }
+  TRY(scratch_reserve(e, e->bsplit, sizeof(float) * h.size()));
+  CU(cudaMemcpyAsync(e->bsplit.p, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  tp->bhi = (const float*)e->bsplit.p;
+  tp->blo = tp->bhi + (size_t)tp->n_pad * kpad;
+  if (!make_map_2d(&tp->map_bhi, tp->bhi, tp->n_pad, kpad, kpad, tp->n_pad)) return RFB_OK;
+  if (!make_map_2d(&tp->map_blo, tp->blo, tp->n_pad, kpad, kpad, tp->n_pad)) return RFB_OK;
+  if (cudaFuncSetAttribute(spatial_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp->smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return RFB_OK;
+  }
+  tp->ok = true;
+  return RFB_OK;
+}
+
+// returns false if this chunk cannot use the tensor-core path (misaligned pointer)
+static bool tc_launch(rfb_engine* e, const TcPlan& tp, const float* d_stim, int64_t nz, int n_pix, int n_q,
+                      float* Z) {
+  if (((uintptr_t)d_stim & 15u) != 0) return false;
+  CUtensorMap map_a;
+  if (!make_map_2d(&map_a, d_stim, (uint64_t)nz, (uint64_t)n_pix, (uint64_t)n_pix, kTcM)) return false;
+  TcArgs a{};
+  a.n_rows = nz;
+  a.n_k_tiles = tp.k_tiles;
+  a.n = n_q;
+  a.n_pad = tp.n_pad;
+  a.n_stages = tp.stages;
+  a.Z = Z;
+  a.ldz = n_q;
+  a.tmem_cols = tp.tmem_cols;
+  const int64_t tiles = (nz + kTcM - 1) / kTcM;
+  const int grid = (int)std::min<int64_t>(tiles, e->num_sms);
+  spatial_project_tc_kernel<<<grid, kTcThreads, tp.smem, e->stream>>>(map_a, tp.map_bhi, tp.map_blo, a);
+  e->launches++;
+  return true;
+}
+
 template <int DFT>
 static void launch_temporal(const TemporalArgs& a, cudaStream_t s) {
   constexpr int TT = DFT <= 8 ? 8 : 4;
@@ -806,6 +920,8 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
     CU(cudaMemcpyAsync(e->stbuf.p, stp.data(), sizeof(float) * stp.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
   }
+  TcPlan tcp;
+  TRY(tc_prepare(e, Sxy, n_pix, n_q, &tcp));
   const float* d_sxy = nullptr;
   if (Sxy) {
     TRY(scratch_reserve(e, e->sxybuf, sizeof(float) * (size_t)n_pix * n_q));
@@ -836,9 +952,11 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
       }
       if (Sxy) {
         TRY(scratch_reserve(e, e->zbuf, sizeof(float) * (size_t)nz * n_q));
-        dim3 grid((unsigned)((nz + kSpTM - 1) / kSpTM), (unsigned)((n_q + kSpTN - 1) / kSpTN));
-        spatial_project_kernel<<<grid, 512, 0, e->stream>>>(d_stim, nz, n_pix, d_sxy, n_q, (float*)e->zbuf.p, n_q);
-        e->launches++;
+        if (!(tcp.ok && tc_launch(e, tcp, d_stim, nz, n_pix, n_q, (float*)e->zbuf.p))) {
+          dim3 grid((unsigned)((nz + kSpTM - 1) / kSpTM), (unsigned)((n_q + kSpTN - 1) / kSpTN));
+          spatial_project_kernel<<<grid, 512, 0, e->stream>>>(d_stim, nz, n_pix, d_sxy, n_q, (float*)e->zbuf.p, n_q);
+          e->launches++;
+        }
         CU(cudaGetLastError());
         d_z = (const float*)e->zbuf.p;
       } else {
