@@ -6,6 +6,10 @@
 // cannot give, so every operand is split  x = hi + lo  with  hi = tf32(x)  (truncation) and
 // lo = x - hi  (exact in fp32), and three tcgen05.mma.kind::tf32 products are accumulated in fp32:
 //     A.B  ~=  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi        (the dropped lo.lo term is ~2^-22 relative)
+// The tensor core adds into its fp32 accumulator with truncation (measured: a bias of about
+// -0.5 ulp per tcgen05.mma), so the chain of accumulations is kept short: the two small cross terms
+// go to their own accumulator, the hi.hi term is dealt round-robin over `n_acc` accumulators, and the
+// epilogue adds the partial sums with round-to-nearest fp32.
 //
 // Structure (one CTA per SM, persistent over 128-row tiles of A; 6 warps):
 //   warp 4      TMA producer: per 32-wide K tile one 2-D bulk-tensor copy of the raw A tile
@@ -39,7 +43,9 @@ struct TcArgs {
   int n_stages;
   float* Z;           // [M x ldz]
   int ldz;
-  int tmem_cols;      // power of two >= 2 * n_pad
+  int tmem_cols;      // power of two >= n_bufs * (n_acc + 1) * n_pad
+  int n_acc;          // independent accumulators of the hi.hi product (round-robin over k-steps)
+  int n_bufs;         // 1 or 2 accumulator sets (2: the epilogue overlaps the next tile's MMAs)
 };
 
 __host__ __device__ inline size_t tc_stage_bytes(int n_pad) {
@@ -181,29 +187,32 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
       int s = 0, buf = 0;
       uint32_t ph = 0, tph = 0;
+      const uint32_t set_cols = (uint32_t)((a.n_acc + 1) * a.n_pad);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         tc::mbar_wait(bar_tempty(buf), tph ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)(buf * a.n_pad);
-        uint32_t acc = 0;
+        const uint32_t d0 = tmem_base + (uint32_t)buf * set_cols;
+        const uint32_t d_small = d0 + (uint32_t)(a.n_acc * a.n_pad);
+        uint32_t small_acc = 0;
+        int step = 0;
         for (int kt = 0; kt < KT; ++kt) {
           tc::mbar_wait(bar_split(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-          for (int ks = 0; ks < kTcK / 8; ++ks) {
+          for (int ks = 0; ks < kTcK / 8; ++ks, ++step) {
             const uint32_t off = (uint32_t)ks * 32u;   // 8 tf32 = 32 bytes along K inside the swizzle atom
             const uint64_t ahi = tc::smem_desc(st_ahi(s) + off), alo = tc::smem_desc(st_alo(s) + off);
             const uint64_t bhi = tc::smem_desc(st_bhi(s) + off), blo = tc::smem_desc(st_blo(s) + off);
-            tc::mma_tf32(d, alo, bhi, idesc, acc);
-            acc = 1;
-            tc::mma_tf32(d, ahi, blo, idesc, 1);
-            tc::mma_tf32(d, ahi, bhi, idesc, 1);
+            tc::mma_tf32(d_small, alo, bhi, idesc, small_acc);
+            small_acc = 1;
+            tc::mma_tf32(d_small, ahi, blo, idesc, 1);
+            tc::mma_tf32(d0 + (uint32_t)((step % a.n_acc) * a.n_pad), ahi, bhi, idesc, step >= a.n_acc ? 1u : 0u);
           }
           tc::commit(bar_empty(s));          // stage reusable once these MMAs have read it
           if (++s == NS) { s = 0; ph ^= 1u; }
         }
-        tc::commit(bar_tfull(buf));          // accumulator complete
-        if (++buf == 2) { buf = 0; tph ^= 1u; }
+        tc::commit(bar_tfull(buf));          // accumulators complete
+        if (++buf == a.n_bufs) { buf = 0; tph ^= 1u; }
       }
     }
   } else {
@@ -234,21 +243,32 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       tc::mbar_wait(bar_tfull(buf), tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const long long row = tile * kTcM + t;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * a.n_pad);
+      const uint32_t set_cols = (uint32_t)((a.n_acc + 1) * a.n_pad);
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * set_cols;
+      // every accumulator needs at least one k-step to be defined: n_acc <= 4 * KT is enforced on the host
       for (int c0 = 0; c0 < a.n_pad; c0 += 16) {
         uint32_t v[16];
-        tc::tmem_ld16(taddr + (uint32_t)c0, v);
+        float sum[16];
+        tc::tmem_ld16(taddr + (uint32_t)(a.n_acc * a.n_pad + c0), v);   // the small cross terms first
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]);
+        for (int k = 0; k < a.n_acc; ++k) {
+          tc::tmem_ld16(taddr + (uint32_t)(k * a.n_pad + c0), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+        }
         if (row < a.n_rows) {
           float* zr = a.Z + row * a.ldz + c0;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < a.n) zr[j] = __uint_as_float(v[j]);
+            if (c0 + j < a.n) zr[j] = sum[j];
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       tc::mbar_arrive(bar_tempty(buf));
-      if (++buf == 2) { buf = 0; tph ^= 1u; }
+      if (++buf == a.n_bufs) { buf = 0; tph ^= 1u; }
     }
   }
 

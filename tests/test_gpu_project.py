@@ -193,3 +193,30 @@ def test_design_errors():
         _glm(distr="binomial")
     with pytest.raises(ValueError):
         _glm().add_design_matrix(np.zeros(50, np.float32), dims=[5], df=[3], smooth="zz")
+
+
+@pytest.mark.parametrize("n,n_pix,n_q", [(300, 64, 16), (1000, 300, 36), (4097, 1024, 100), (70001, 300, 36),
+                                         (513, 128, 128), (260, 96, 8)])
+def test_tensor_core_spatial_projection(n, n_pix, n_q):
+    """K1a on tcgen05 (TMA-fed 3xTF32, TMEM accumulators) against fp64 and the CUDA-core kernel."""
+    from rfest_b200.engine import Block, Engine
+
+    eng = Engine.get()
+    rng = np.random.default_rng(n_pix + n_q)
+    stim = rng.standard_normal((n, n_pix)).astype(np.float32)
+    Sxy = (rng.standard_normal((n_pix, n_q)) / np.sqrt(n_pix)).astype(np.float32)
+    out = {}
+    try:
+        for tc in (0, 1):
+            eng.set_option("project_tc", tc)
+            blk = Block(eng, n, n_q)
+            blk.project(stim, dst_row0=0, n_out=n, col0=0, src0=0, n_raw_total=n, n_pix=n_pix, first_t=0,
+                        nlag=1, shift=0, St=np.ones((1, 1), np.float32), Sxy=Sxy)
+            out[tc] = blk.read()
+    finally:
+        eng.set_option("project_tc", 1)
+    ref = stim.astype(np.float64) @ Sxy.astype(np.float64)
+    scale = np.abs(ref).max()
+    assert np.abs(out[0] - ref).max() <= 2e-6 * scale
+    assert np.abs(out[1] - ref).max() <= 2e-6 * scale          # fp32-level accuracy from tf32 tensor cores
+    assert not np.array_equal(out[0], out[1])                   # i.e. the tensor-core path really ran
