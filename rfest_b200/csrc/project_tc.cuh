@@ -11,16 +11,16 @@
 // go to their own accumulator, the hi.hi term is dealt round-robin over `n_acc` accumulators, and the
 // epilogue adds the partial sums with round-to-nearest fp32.
 //
-// Structure (one CTA per SM, persistent over 128-row tiles of A; 6 warps):
-//   warp 4      TMA producer: per 32-wide K tile one 2-D bulk-tensor copy of the raw A tile
+// Structure (one CTA per SM, persistent over 128-row tiles of A; 10 warps):
+//   warp 8      TMA producer: per 32-wide K tile one 2-D bulk-tensor copy of the raw A tile
 //               (128 x 32 fp32, SWIZZLE_128B) and of the pre-split B_hi / B_lo tiles (N x 32), all
 //               signalling the stage's mbarrier with their byte counts.
-//   warps 0-3   splitters: turn the landed raw A tile into A_hi (in place) and A_lo with
+//   warps 4-7   splitters: turn the landed raw A tile into A_hi (in place) and A_lo with
 //               conflict-free 16-byte LDS/STS (the split is element-wise, hence layout-agnostic),
-//               fence the generic->async proxy and hand the stage to the MMA warp.  After the last
-//               K tile of a row tile they are the epilogue: tcgen05.ld the 128 x N fp32 accumulator
-//               out of TMEM (lane = row) and store Z.
-//   warp 5      MMA issuer: one elected thread issues 12 tcgen05.mma (4 k-steps x 3 products) per
+//               fence the generic->async proxy and hand the stage to the MMA warp.
+//   warps 0-3   epilogue: tcgen05.ld the partial 128 x N fp32 accumulators out of TMEM (lane = row),
+//               add them and store Z with 16-byte stores, while the next tile is already running.
+//   warp 9      MMA issuer: one elected thread issues 12 tcgen05.mma (4 k-steps x 3 products) per
 //               stage from shared-memory descriptors into one of two TMEM accumulator buffers,
 //               tcgen05.commit releases the stage / publishes the accumulator.
 #pragma once
@@ -33,7 +33,7 @@ namespace rfb {
 
 constexpr int kTcM = 128;     // rows of A per tile = TMEM lanes
 constexpr int kTcK = 32;      // K tile: 32 fp32 = 128 bytes = one swizzle atom
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;   // warps 0-3 epilogue (TMEM lanes), 4-7 splitters, 8 TMA, 9 MMA
 
 struct TcArgs {
   long long n_rows;   // M
@@ -149,7 +149,7 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {   // TMEM allocation by one warp; it also owns the deallocation
+  if (warp == 9) {   // TMEM allocation by one warp; it also owns the deallocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -163,7 +163,7 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
   const long long n_tiles = (a.n_rows + kTcM - 1) / kTcM;
   const int KT = a.n_k_tiles;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================= TMA producer =================
     if (lane == 0) {
       int s = 0;
@@ -180,7 +180,7 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================= MMA issuer =================
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = n_pad, M = 128
@@ -215,11 +215,11 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         if (++buf == a.n_bufs) { buf = 0; tph ^= 1u; }
       }
     }
-  } else {
-    // ================= splitters + epilogue (warps 0-3, 128 threads) =================
-    const int t = threadIdx.x;   // 0..127 = TMEM lane = row inside the tile
-    int s = 0, buf = 0;
-    uint32_t ph = 0, tph = 0;
+  } else if (warp >= 4) {
+    // ================= splitters (warps 4-7, 128 threads) =================
+    const int t = threadIdx.x - 128;
+    int s = 0;
+    uint32_t ph = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kt = 0; kt < KT; ++kt) {
         tc::mbar_wait(bar_raw(s), ph);
@@ -239,7 +239,14 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         tc::mbar_arrive(bar_split(s));
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
-      // epilogue of this row tile
+    }
+  } else {
+    // ================= epilogue (warps 0-3: thread = TMEM lane = row inside the tile) =================
+    const int t = threadIdx.x;
+    int buf = 0;
+    uint32_t tph = 0;
+    const bool vec_ok = (a.ldz % 4) == 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       tc::mbar_wait(bar_tfull(buf), tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const long long row = tile * kTcM + t;
@@ -262,8 +269,15 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         if (row < a.n_rows) {
           float* zr = a.Z + row * a.ldz + c0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < a.n) zr[j] = sum[j];
+          for (int j = 0; j < 16; j += 4) {
+            if (vec_ok && c0 + j + 3 < a.n) {
+              *reinterpret_cast<float4*>(zr + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+            } else {
+#pragma unroll
+              for (int jj = j; jj < j + 4; ++jj)
+                if (c0 + jj < a.n) zr[jj] = sum[jj];
+            }
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -274,7 +288,7 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
 }

@@ -936,8 +936,9 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
     d_sxy = (const float*)e->sxybuf.p;
   }
 
-  int64_t chunk = (int64_t)(64u << 20) / n_pix;  // ~256 MB of staged stimulus per chunk
-  chunk = std::min<int64_t>(std::max<int64_t>(chunk, 4096), 1 << 20);
+  // rows per slab: host input is staged through <= 256 MB; device input only needs the Z scratch (<= 1 GB)
+  int64_t chunk = on_device ? (int64_t)(256u << 20) / n_q : (int64_t)(64u << 20) / n_pix;
+  chunk = std::min<int64_t>(std::max<int64_t>(chunk, 4096), on_device ? (1 << 23) : (1 << 20));
   for (int64_t k0 = 0; k0 < n_out; k0 += chunk) {
     const int64_t kc = std::min<int64_t>(chunk, n_out - k0);
     int64_t lo = first_t + k0 - front, hi = first_t + k0 + kc - 1 + nlag - 1 - front;
