@@ -166,6 +166,12 @@ int rfb_model_n_params(rfb_model* m, int* n_coef_total, int* n_intercepts);
 int rfb_model_eval(rfb_model* m, int kind, const float* b, const double* intercepts,
                    float* r_out, double* sums);
 
+/* Normal-equation pieces for the least-squares initialisation (compute_mle, _glm.py:438-537):
+ * over the concatenated, padded design columns of data set `kind` (ctot of them, slot after slot),
+ * gram = XS^T XS [ctot x ctot], colsum = XS^T 1 [ctot], xty = XS^T y [ctot], all float64 and
+ * all-reduced over ranks.  Any output may be NULL; with all three NULL only *ctot is set. */
+int rfb_model_gram(rfb_model* m, int kind, double* gram, double* colsum, double* xty, int* ctot);
+
 /* ---- fit loop (GLM.optimize, _glm.py:644-836) --------------------------------------------- */
 /* Prepare `max_iters` iterations from the current parameters with zeroed Adam state:
  *   step_sizes[max_iters]  per-iteration learning rate (a constant or a schedule evaluated

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "gram.cuh"
 #include "project.cuh"
 #include "project_tc.cuh"
 #include "sweep.cuh"
@@ -1252,6 +1253,59 @@ extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const doub
     sums[RFB_SUM_YY] = ds.syy;
   }
   return RFB_OK;
+}
+
+extern "C" int rfb_model_gram(rfb_model* m, int kind, double* gram, double* colsum, double* xty, int* ctot_out) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  DataSet& ds = m->data[kind];
+  if (!ds.bound) return fail(RFB_ERR_STATE, "no data bound for kind %d", kind);
+  TRY(ensure_plan(m));
+  const Plan& p = m->plan;
+  if (ctot_out) *ctot_out = p.ctot;
+  if (!gram && !colsum && !xty) return RFB_OK;     // size query
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  GramArgs a{};
+  a.n_slots = p.n_slots;
+  for (int s = 0; s < p.n_slots; ++s) {
+    rfb_block* b = s < ds.n_slots ? ds.blocks[s] : nullptr;
+    a.slot_ptr[s] = b ? b->d : nullptr;
+    a.slot_ld[s] = b ? b->ld : 0;
+  }
+  for (int s = 0; s <= p.n_slots; ++s) a.slot_col0[s] = 4 * p.slot_chunk0[s];
+  a.ctot = p.ctot;
+  a.n_rows = ds.n;
+  a.y = ds.has_y ? ds.y : nullptr;
+  a.n_tiles = (p.ctot + kGramTile - 1) / kGramTile;
+  a.n_pairs = a.n_tiles * (a.n_tiles + 1) / 2;
+  // enough slabs to fill the chip about twice, but never shorter than 4096 rows
+  int slabs = std::max(1, (2 * e->num_sms + a.n_pairs - 1) / a.n_pairs);
+  slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, ds.n / 4096));
+  a.n_slabs = slabs;
+  const size_t n_entries = (size_t)p.ctot * p.ctot + 2 * (size_t)p.ctot;
+  double *d_part = nullptr, *d_out = nullptr;
+  CU(cudaMalloc(&d_part, sizeof(double) * n_entries * slabs));
+  CU(cudaMalloc(&d_out, sizeof(double) * n_entries));
+  a.part = d_part;
+  gram_kernel<<<dim3(a.n_pairs, slabs), 256, 0, e->stream>>>(a);
+  gram_reduce_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, e->stream>>>(d_part, slabs, (long long)n_entries, d_out);
+  e->launches += 2;
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  int rc = RFB_OK;
+  if (ce != cudaSuccess) rc = fail(RFB_ERR_CUDA, "gram kernel failed: %s", cudaGetErrorString(ce));
+  if (rc == RFB_OK) rc = allreduce_device_f64(e, d_out, n_entries);
+  if (rc == RFB_OK) {
+    const size_t cc = (size_t)p.ctot * p.ctot;
+    if (gram) cudaMemcpyAsync(gram, d_out, sizeof(double) * cc, cudaMemcpyDeviceToHost, e->stream);
+    if (colsum) cudaMemcpyAsync(colsum, d_out + cc, sizeof(double) * p.ctot, cudaMemcpyDeviceToHost, e->stream);
+    if (xty) cudaMemcpyAsync(xty, d_out + cc + p.ctot, sizeof(double) * p.ctot, cudaMemcpyDeviceToHost, e->stream);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(RFB_ERR_CUDA, "gram copy-back failed");
+  }
+  cudaFree(d_part);
+  cudaFree(d_out);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

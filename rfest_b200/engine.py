@@ -293,6 +293,18 @@ class DeviceModel:
             sums.ctypes.data_as(C.c_void_p)))
         return r, sums
 
+    def gram(self, kind):
+        """-> (G [ctot x ctot], colsum [ctot], xty [ctot]) in float64 over the padded, concatenated
+        design columns (slot after slot); see rfb_model_gram."""
+        c = C.c_int()
+        check(self.lib.rfb_model_gram(self.handle, _lib.KIND[kind], None, None, None, C.byref(c)))
+        G = np.empty((c.value, c.value), dtype=np.float64)
+        s = np.empty(c.value, dtype=np.float64)
+        t = np.empty(c.value, dtype=np.float64)
+        check(self.lib.rfb_model_gram(self.handle, _lib.KIND[kind], G.ctypes.data_as(C.c_void_p),
+                                      s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.byref(c)))
+        return G, s, t
+
     # ---- fit loop ------------------------------------------------------------------------
     def fit_begin(self, step_sizes, alpha, beta, metric):
         steps = np.ascontiguousarray(step_sizes, dtype=np.float64)

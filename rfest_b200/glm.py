@@ -373,10 +373,69 @@ class GLM:
         self._initialize_p0(method, add_noise_to_mle=add_noise_to_mle, random_seed=random_seed)
 
     def compute_mle(self, y, compute_ci=True):
-        """_glm.py:438-537 (least squares on the ones-augmented design)."""
-        raise NotImplementedError(
-            "initialize(method='mle') is not implemented in this engine yet "
-            "(SURVEY.md section 8f, rank 1); use method='random' or set `p0`.")
+        """_glm.py:438-537: least squares on the ones-augmented column stack
+        A = [1 | 1 XS_f1 | 1 XS_f2 ...] through the normal equations and `lstsq`.
+
+        The device computes the float64 Gram pieces XS^T XS, XS^T 1, XS^T y in one pass over the
+        designs (csrc/gram.cuh; all-reduced over ranks); the (P+F+1)^2 system is assembled and
+        solved on the host in float64, as the reference does (its ones are float64)."""
+        if type(y) is dict:
+            y_train = y["train"]
+            if len(y_train) == 0:
+                raise ValueError("Training set is empty after burned in.")
+            y_dev = y.get("dev", None)
+        else:
+            y_train, y_dev = y, None
+        if y_train is None:
+            raise ValueError("`y` is needed for the maximum-likelihood initialisation.")
+        self.y["train"] = self._trim_y(y_train, "train")
+        if len(self.y["train"]) == 0:
+            raise ValueError("Training set is empty after burned in.")
+        if y_dev is not None:
+            self.y["dev"] = self._trim_y(y_dev, "dev")
+            if len(self.y["dev"]) == 0:
+                raise ValueError("Dev set is empty after burned in.")
+        self._dirty = True
+        self._sync()
+        G, colsum, xty = self._dm.gram("train")
+        n = float(self._n_trim["train"])
+        sum_y = float(np.sum(self.y["train"], dtype=np.float64))
+        if self.engine.world > 1:
+            sum_y = float(self.engine.allreduce_f64([sum_y])[0])
+
+        # column k of A is either a ones column (-1) or design column c of the concatenated blocks
+        cols = [-1]
+        for name in self.filter_names:
+            c0 = self._slot_col0[self._slot_of[name]]
+            cols += [-1] + list(range(c0, c0 + self.n_features[name]))
+        cols = np.asarray(cols)
+        ones = cols < 0
+        dc = np.where(ones, 0, cols)
+        XtX = G[np.ix_(dc, dc)]
+        XtX[ones, :] = np.where(ones, n, colsum[dc])[None, :]
+        XtX[:, ones] = np.where(ones, n, colsum[dc])[:, None]
+        Xty = np.where(ones, sum_y, xty[dc])
+        mle = np.linalg.lstsq(XtX, Xty, rcond=None)[0]                            # _glm.py:480
+
+        self.b["mle"], self.w["mle"], self.intercept["mle"] = {}, {}, {}
+        edges = np.cumsum([0] + [self.n_features[name] + 1 for name in self.filter_names])
+        self.idx = [np.array((edges[i], edges[i + 1])) for i in range(len(edges) - 1)]
+        for i, name in enumerate(self.filter_names):                             # _glm.py:495-502
+            seg = mle[edges[i]:edges[i + 1]][:, np.newaxis].astype(np.float32)
+            self.intercept["mle"][name] = seg[0]
+            if name in self.S:
+                self.b["mle"][name] = seg[1:]
+                self.w["mle"][name] = (self.S[name] @ seg[1:]).astype(np.float32)
+            else:
+                self.w["mle"][name] = seg[1:]
+        self.intercept["mle"]["global"] = mle[0]
+        self.p["mle"] = {name: (self.b["mle"][name] if name in self.S else self.w["mle"][name])
+                         for name in self.filter_names}
+        self.p["mle"]["intercept"] = self.intercept["mle"]
+        self.y_pred["mle"] = {"train": self.forwardpass(self.p["mle"], kind="train")}
+        if y_dev is not None:
+            self.y_pred["mle"]["dev"] = self.forwardpass(self.p["mle"], kind="dev")
+        self.mle_computed = True
 
     # ------------------------------------------------------------------------------------
     # device model plumbing
@@ -417,6 +476,10 @@ class GLM:
         for name in self.filter_names:
             dm.add_filter(slot_of[name], self.filter_nonlinearity[name], self.n_features[name])
         self._order = list(self.filter_names)
+        self._slot_of = slot_of
+        self._slot_col0 = [0]
+        for blk in slots:                       # padded column offset of every slot in the concatenated design
+            self._slot_col0.append(self._slot_col0[-1] + blk.ld)
         for kind, blocks in self._blocks.items():
             per_slot = [None] * len(slots)
             for name, blk in blocks.items():

@@ -297,3 +297,108 @@ def test_nan_raises_like_debug_nans():
         m.fit(y=y, num_iters=3, verbose=0, tolerance=0)
     with pytest.raises(ValueError):
         GLM().fit(num_iters=1)
+
+
+# ---- least-squares initialisation + the reference's own test recipe (tests/test_glm.py) ------------
+def _fit_like_reference(cls, Xy_train, dims, Xy_dev=None, history=False, out_nl="none", subunits=1):
+    """`_fit_glm` of the reference's tests/test_glm.py:14-73 (method='mle', 300 iterations)."""
+    df = helpers.df_rule(dims)
+    model = cls(distr="gaussian", output_nonlinearity=out_nl)
+    model.add_design_matrix(Xy_train[0], dims=list(dims), df=df, smooth="cr", kind="train",
+                            filter_nonlinearity="none", name="stimulus")
+    if Xy_dev is not None:
+        model.add_design_matrix(Xy_dev[0], dims=list(dims), df=df, name="stimulus", kind="dev")
+    if history:
+        model.add_design_matrix(Xy_train[1], dims=[5], df=[3], smooth="cr", kind="train",
+                                filter_nonlinearity="none", name="history")
+        if Xy_dev is not None:
+            model.add_design_matrix(Xy_dev[1], dims=[5], df=[3], kind="dev", name="history")
+    fit_y = {"train": Xy_train[1]}
+    if Xy_dev is not None:
+        fit_y["dev"] = Xy_dev[1]
+    model.initialize(num_subunits=subunits, dt=1.0, method="mle", random_seed=42, compute_ci=False,
+                     y=Xy_train[1])
+    model.fit(y=fit_y, num_iters=300, verbose=0, step_size=0.03, beta=0.001, metric="mse")
+    return model
+
+
+def _mse_uvec(w, w_true):
+    return np.mean((helpers.uvec(np.asarray(w, np.float64)).ravel() - helpers.uvec(w_true.flatten())) ** 2)
+
+
+def test_mle_initialisation_matches_oracle():
+    from rfest_b200 import GLM
+
+    w_true, X, y, dims = helpers.data_3d_stim()
+    y = y + 0.05 * np.random.default_rng(0).standard_normal(len(y))
+    tr, dv, _ = helpers.split(X, y, 0.7, 0.3)
+    models = []
+    for cls in (GLM, OracleGLM):
+        m = cls(distr="gaussian", output_nonlinearity="none")
+        m.add_design_matrix(tr[0], dims=list(dims), df=helpers.df_rule(dims), smooth="cr", name="stimulus")
+        m.add_design_matrix(dv[0], name="stimulus", kind="dev")
+        m.add_design_matrix(tr[1], dims=[5], df=[3], smooth="cr", name="history")
+        m.add_design_matrix(dv[1], name="history", kind="dev")
+        m.initialize(method="mle", y={"train": tr[1], "dev": dv[1]}, compute_ci=False)
+        models.append(m)
+    g, o = models
+    assert g.mle_computed and set(g.p["mle"]) == set(o.p["mle"])
+    for kind in ("train", "dev"):
+        assert _wrel(g.y_pred["mle"][kind], o.y_pred["mle"][kind]) < 1e-4
+    assert _wrel(g.w["mle"]["stimulus"], o.w["mle"]["stimulus"]) < 1e-3
+    # p0 is the MLE (no noise), so the first train cost is the least-squares residual
+    g.fit(y={"train": tr[1], "dev": dv[1]}, num_iters=3, verbose=0, step_size=1e-4, beta=0.0, metric="mse")
+    o.fit(y={"train": tr[1], "dev": dv[1]}, num_iters=3, verbose=0, step_size=1e-4, beta=0.0, metric="mse")
+    assert abs(g.cost_train[0] - o.cost_train[0]) < 1e-4 * abs(o.cost_train[0])
+
+
+def test_reference_recipe_3d_stim():                       # tests/test_glm.py:76-87
+    from rfest_b200 import GLM
+
+    w_true, X, y, dims = helpers.data_3d_stim()
+    model = _fit_like_reference(GLM, (X, y), dims)
+    assert model.score(X, y, metric="corrcoef") > 0.4
+    assert _mse_uvec(model.w["opt"]["stimulus"], w_true) < 0.01
+
+
+def test_reference_recipe_train_dev_test():                # tests/test_glm.py:90-107
+    from rfest_b200 import GLM
+
+    w_true, X, y, dims = helpers.data_3d_stim()
+    tr, dv, te = helpers.split(X, y, 0.6, 0.2)
+    model = _fit_like_reference(GLM, tr, dims, Xy_dev=dv)
+    assert model.score(tr[0], tr[1], metric="corrcoef") > 0.4
+    assert model.score(dv[0], dv[1], metric="corrcoef") > 0.3
+    assert model.score(te[0], te[1], metric="corrcoef") > 0.2
+    assert _mse_uvec(model.w["opt"]["stimulus"], w_true) < 0.01
+
+
+def test_reference_recipe_output_nonlinearity():           # tests/test_glm.py:110-125
+    from rfest_b200 import GLM
+
+    w_true, X, y, dims = helpers.data_3d_stim()
+    model = _fit_like_reference(GLM, (X, y), dims, out_nl="exponential")
+    assert model.score(X, y, metric="corrcoef") > 0.4
+    assert _mse_uvec(model.w["opt"]["stimulus"], w_true) < 0.01
+
+
+def test_reference_recipe_two_subunits():                  # tests/test_glm.py:128-149
+    from rfest_b200 import GLM
+
+    w_true, X, y, dims = helpers.data_3d_stim()
+    model = _fit_like_reference(GLM, (X, y), dims, subunits=2)
+    assert model.score(X, y, metric="corrcoef") > 0.4
+    w = np.asarray(model.w["opt"]["stimulus_s0"]) + np.asarray(model.w["opt"]["stimulus_s1"])
+    assert _mse_uvec(w, w_true) < 0.01
+
+
+def test_reference_recipe_history_filter():                # tests/test_glm.py:152-180
+    from rfest_b200 import GLM
+
+    w_true, X, y, dims = helpers.data_3d_stim()
+    tr, dv, te = helpers.split(X, y, 0.6, 0.2)
+    model = _fit_like_reference(GLM, tr, dims, Xy_dev=dv, history=True)
+    assert model.score({"stimulus": tr[0], "history": tr[1]}, tr[1], metric="corrcoef") > 0.4
+    assert model.score({"stimulus": dv[0], "history": dv[1]}, dv[1], metric="corrcoef") > 0.3
+    assert model.score({"stimulus": te[0], "history": te[1]}, te[1], metric="corrcoef") > 0.2
+    assert _mse_uvec(model.w["opt"]["stimulus"], w_true) < 0.01
