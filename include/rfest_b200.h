@@ -105,6 +105,13 @@ int rfb_host_free(void* p);
 int rfb_comm_unique_id(void* out128);
 int rfb_engine_comm_init(rfb_engine* e, const void* id128, int rank, int world);
 int rfb_engine_comm_info(rfb_engine* e, int* rank, int* world);
+/* One-shot exchange over NVLink peer memory, replacing the NCCL call inside the fit iteration:
+ * the reduction kernel stores each rank's vector into every peer's buffer (P2P stores) and the
+ * update kernel waits on flags and adds the slots in rank order.  create() allocates this
+ * rank's buffer and returns its 64-byte CUDA IPC handle; the caller all-gathers the handles
+ * (rank order) and passes all of them to connect().  Optional: without it the engine uses NCCL. */
+int rfb_engine_xchg_create(rfb_engine* e, void* handle64);
+int rfb_engine_xchg_connect(rfb_engine* e, const void* handles);
 /* in-place sum all-reduce of a host double vector over the engine's communicator
  * (no-op when there is none); used for the one-time constants n, sum y, sum y^2 */
 int rfb_engine_allreduce_f64(rfb_engine* e, double* host_inout, int count);

@@ -46,6 +46,8 @@ SIGNATURES = {
     "rfb_comm_unique_id": (_i, [_p]),
     "rfb_engine_comm_init": (_i, [_p, _p, _i, _i]),
     "rfb_engine_comm_info": (_i, [_p, _ip, _ip]),
+    "rfb_engine_xchg_create": (_i, [_p, _p]),
+    "rfb_engine_xchg_connect": (_i, [_p, _p]),
     "rfb_engine_allreduce_f64": (_i, [_p, _dp, _i]),
     "rfb_block_create": (_i, [_p, _i64, _i, C.POINTER(_p)]),
     "rfb_block_destroy": (_i, [_p]),

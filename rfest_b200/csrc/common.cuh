@@ -49,6 +49,23 @@ struct SweepArgs {
   int n_stages;                     // staged variant: depth of each warp's copy ring
 };
 
+// One-shot exchange over NVLink peer memory (multi-GPU): every rank owns a buffer
+//   [flags: 2 parities x kMaxRanks uint64][data: 2 parities x world x cap doubles]
+// mapped into all peers (CUDA IPC).  The reduction kernel of rank r stores its reduced vector
+// into slot r of EVERY rank's buffer and then publishes the iteration's sequence number in the
+// flag; the update kernel waits for all ranks' flags and adds the slots in rank order (so all
+// ranks compute bit-identical sums).  Two parities: a rank can run at most one iteration ahead.
+constexpr int kMaxRanks = 8;
+constexpr int kXchgDataOffset = 256;   // bytes: flags first
+struct XchgArgs {
+  unsigned char* peer[kMaxRanks];      // every rank's buffer (peer[rank] is the local one)
+  int world;                           // 1: exchange disabled
+  int rank;
+  long long cap;                       // doubles per slot
+  unsigned long long* seq;             // local device counter: completed exchanges
+  unsigned int* done;                  // local device counter for "last CTA" detection
+};
+
 __host__ __device__ inline int sweep_num_entries(int H, int n_chunks) {
   return H * n_chunks * 4 + kNumScalars;
 }

@@ -111,6 +111,14 @@ struct rfb_engine {
   int rank = 0, world = 1;
   Scratch stage, zbuf, stbuf, sxybuf, small, bsplit;
   int project_tc = 1;     // spatial projection on tensor cores (tcgen05, 3xTF32) when the shape allows
+  // one-shot NVLink exchange (multi-GPU): local buffer, peers' mappings, device counters
+  int use_xchg = 1;
+  bool xchg_ready = false;
+  unsigned char* xchg_local = nullptr;
+  unsigned char* xchg_peer[kMaxRanks] = {};
+  unsigned long long* xchg_seq = nullptr;
+  unsigned int* xchg_done = nullptr;
+  long long xchg_cap = 8192;   // doubles per slot
   // sweep launch shape (tunable: rfb_engine_set_option / RFB_SWEEP_* environment variables)
   int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
   int sweep_stages = 0;   // depth of each warp's copy ring (0: sized for ~112 KB in flight per SM)
@@ -583,6 +591,7 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   if (const char* v = getenv("RFB_SWEEP_WARPS")) e->sweep_warps = atoi(v);
   if (const char* v = getenv("RFB_SWEEP_CTAS")) e->sweep_ctas = atoi(v);
   if (const char* v = getenv("RFB_PROJECT_TC")) e->project_tc = atoi(v);
+  if (const char* v = getenv("RFB_XCHG")) e->use_xchg = atoi(v);
   *out = e;
   return RFB_OK;
 }
@@ -595,6 +604,7 @@ extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) 
   else if (k == "sweep_warps") e->sweep_warps = value;
   else if (k == "sweep_ctas") e->sweep_ctas = value;
   else if (k == "project_tc") e->project_tc = value;
+  else if (k == "xchg") e->use_xchg = value;
   else return fail(RFB_ERR_INVALID, "unknown option '%s'", key);
   return RFB_OK;
 }
@@ -673,6 +683,66 @@ extern "C" int rfb_engine_comm_info(rfb_engine* e, int* rank, int* world) {
   if (rank) *rank = e->rank;
   if (world) *world = e->world;
   return RFB_OK;
+}
+
+static size_t xchg_bytes(const rfb_engine* e) {
+  return (size_t)kXchgDataOffset + sizeof(double) * 2 * kMaxRanks * (size_t)e->xchg_cap;
+}
+
+extern "C" int rfb_engine_xchg_create(rfb_engine* e, void* handle64) {
+  if (!e || !handle64) return fail(RFB_ERR_INVALID, "NULL argument");
+  TRY(use_device(e));
+  if (!e->xchg_local) {
+    CU(cudaMalloc(&e->xchg_local, xchg_bytes(e)));
+    CU(cudaMemset(e->xchg_local, 0, xchg_bytes(e)));
+    CU(cudaMalloc(&e->xchg_seq, sizeof(unsigned long long)));
+    CU(cudaMalloc(&e->xchg_done, sizeof(unsigned int)));
+    CU(cudaMemset(e->xchg_seq, 0, sizeof(unsigned long long)));
+    CU(cudaMemset(e->xchg_done, 0, sizeof(unsigned int)));
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, e->xchg_local));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, sizeof(h));
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_xchg_connect(rfb_engine* e, const void* handles) {
+  if (!e || !handles) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (!e->xchg_local) return fail(RFB_ERR_STATE, "rfb_engine_xchg_create has not been called");
+  if (e->world < 2 || e->world > kMaxRanks) return fail(RFB_ERR_UNSUPPORTED, "exchange needs 2..%d ranks", kMaxRanks);
+  TRY(use_device(e));
+  for (int q = 0; q < e->world; ++q) {
+    if (q == e->rank) {
+      e->xchg_peer[q] = e->xchg_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * q, sizeof(h));
+    void* p = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RFB_ERR_CUDA, "cannot map rank %d's exchange buffer: %s", q, cudaGetErrorString(ce));
+    }
+    e->xchg_peer[q] = (unsigned char*)p;
+  }
+  e->xchg_ready = true;
+  return RFB_OK;
+}
+
+static XchgArgs xchg_args(const rfb_engine* e, bool on) {
+  XchgArgs x{};
+  x.world = 1;
+  if (on) {
+    for (int q = 0; q < e->world; ++q) x.peer[q] = e->xchg_peer[q];
+    x.world = e->world;
+    x.rank = e->rank;
+    x.cap = e->xchg_cap;
+    x.seq = e->xchg_seq;
+    x.done = e->xchg_done;
+  }
+  return x;
 }
 
 static int allreduce_device_f64(rfb_engine* e, double* d, size_t count) {
@@ -1344,18 +1414,36 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   if (f.has_dev) TRY(launch_sweep(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false, r_dev));
   if (ev) CU(cudaEventRecord(ev[2], e->stream));
   const int tail = p.Ht * p.ctot;
-  if (final_only) {
-    TRY(launch_reduce(m, RFB_KIND_TRAIN, tail, kNumScalars, f.fin + tail,
-                      f.has_dev ? RFB_KIND_DEV : -1, tail, kNumScalars, f.fin + p.NE));
-    TRY(allreduce_device_f64(e, f.fin + tail, 2 * kNumScalars));   // train tail + dev scalars are adjacent
+  const bool xchg = e->comm && e->use_xchg && e->xchg_ready && (long long)p.NE + kNumScalars <= e->xchg_cap;
+  const int lo = final_only ? tail : 0;
+  const int n_train = p.NE - lo;
+  long long sum_lo = lo, sum_hi = (long long)p.NE + (f.has_dev ? kNumScalars : 0);
+  if (xchg) {
+    // reduction fused with the exchange: sums go straight into every rank's buffer over NVLink
+    ReduceSeg s0{m->sb[RFB_KIND_TRAIN].cta_part + lo, m->sb[RFB_KIND_TRAIN].grid, p.NE, n_train, nullptr};
+    const int blocks0 = (n_train + kReduceEx - 1) / kReduceEx;
+    ReduceSeg s1{nullptr, 0, 0, 0, nullptr};
+    int blocks1 = 0;
+    if (f.has_dev) {
+      s1 = ReduceSeg{m->sb[RFB_KIND_DEV].cta_part + tail, m->sb[RFB_KIND_DEV].grid, p.NE, kNumScalars, nullptr};
+      blocks1 = (kNumScalars + kReduceEx - 1) / kReduceEx;
+    }
+    reduce_exchange_kernel<<<blocks0 + blocks1, dim3(kReduceEx, kReduceEy), 0, e->stream>>>(
+        s0, s1, blocks0, (long long)lo, (long long)p.NE, xchg_args(e, true));
+    e->launches++;
+    CU(cudaGetLastError());
   } else {
-    TRY(launch_reduce(m, RFB_KIND_TRAIN, 0, p.NE, f.fin, f.has_dev ? RFB_KIND_DEV : -1, tail,
+    TRY(launch_reduce(m, RFB_KIND_TRAIN, lo, n_train, f.fin + lo, f.has_dev ? RFB_KIND_DEV : -1, tail,
                       kNumScalars, f.fin + p.NE));
-    TRY(allreduce_device_f64(e, f.fin, (size_t)p.NE + kNumScalars));
+    TRY(allreduce_device_f64(e, f.fin + lo, (size_t)(sum_hi - lo)));
   }
   if (ev) CU(cudaEventRecord(ev[3], e->stream));
   UpdateArgs ua = f.ua;
   ua.final_only = final_only ? 1 : 0;
+  ua.x = xchg_args(e, xchg);
+  ua.fin_local = f.fin;
+  ua.sum_lo = sum_lo;
+  ua.sum_hi = sum_hi;
   update_kernel<<<1, kUpdateThreads, 0, e->stream>>>(ua);
   e->launches++;
   CU(cudaGetLastError());

@@ -626,4 +626,53 @@ reduce_partials_kernel(ReduceSeg s0, ReduceSeg s1, int blocks0) {
   }
 }
 
+// The same reduction fused with the multi-GPU exchange: instead of a local vector, the sums are
+// stored straight into this rank's slot of every peer's exchange buffer (P2P stores over
+// NVLink); the last CTA to finish publishes the sequence number to all peers.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kReduceEx * kReduceEy)
+reduce_exchange_kernel(ReduceSeg s0, ReduceSeg s1, int blocks0, long long off0, long long off1, XchgArgs x) {
+  const bool first = (int)blockIdx.x < blocks0;
+  const ReduceSeg s = first ? s0 : s1;
+  const long long off = first ? off0 : off1;
+  const int b = first ? blockIdx.x : blockIdx.x - blocks0;
+  __shared__ double sm[kReduceEy][kReduceEx];
+  const unsigned long long seq = *x.seq + 1ull;
+  const int parity = (int)(seq & 1ull);
+  const int e = b * kReduceEx + threadIdx.x;
+  double acc = 0.0;
+  if (e < s.n_entries) {
+    for (int p = threadIdx.y; p < s.n_parts; p += kReduceEy) acc += s.part[(size_t)p * s.stride + e];
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < s.n_entries) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kReduceEy; ++k) t += sm[k][threadIdx.x];
+    const long long slot = ((long long)parity * x.world + x.rank) * x.cap + off + e;
+    for (int q = 0; q < x.world; ++q)
+      reinterpret_cast<double*>(x.peer[q] + kXchgDataOffset)[slot] = t;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned int prev = atomicAdd(x.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *x.done = 0u;
+      __threadfence_system();
+      for (int q = 0; q < x.world; ++q)
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(x.peer[q]) + parity * kMaxRanks + x.rank, seq);
+    }
+  }
+}
+
 }  // namespace rfb

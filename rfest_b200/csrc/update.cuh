@@ -48,6 +48,9 @@ struct UpdateArgs {
   int* it;              // device-side iteration counter
   int max_iters;
   int final_only;       // 1: only complete trace entry it-1 (no cost, no update)
+  XchgArgs x;           // multi-GPU one-shot exchange (x.world == 1: fin_* already hold the totals)
+  double* fin_local;    // [sum_hi] where the exchanged totals are written (= fin_train)
+  long long sum_lo, sum_hi;   // entries of the exchanged vector this call needs
 };
 
 __device__ inline double score_from_sums(int metric, const double* s, double n, double sy, double syy) {
@@ -102,9 +105,36 @@ __global__ void __launch_bounds__(kUpdateThreads) publish_params_kernel(const Up
   publish_params(a);
 }
 
+__device__ inline unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(kUpdateThreads) update_kernel(const UpdateArgs a) {
   __shared__ double sm[kUpdateThreads / 32];
   __shared__ float s_bc[2];
+  if (a.x.world > 1) {
+    // wait until every rank has published this iteration's vector in my buffer, then add the
+    // slots in rank order (identical on all ranks)
+    const unsigned long long seq = *a.x.seq + 1ull;
+    const int parity = (int)(seq & 1ull);
+    unsigned char* mine = a.x.peer[a.x.rank];
+    if ((int)threadIdx.x < a.x.world) {
+      const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mine) + parity * kMaxRanks + threadIdx.x;
+      while (ld_acquire_sys(flag) < seq) {
+      }
+    }
+    __syncthreads();
+    const double* data = reinterpret_cast<const double*>(mine + kXchgDataOffset) + (long long)parity * a.x.world * a.x.cap;
+    for (long long e = a.sum_lo + threadIdx.x; e < a.sum_hi; e += blockDim.x) {
+      double t = 0.0;
+      for (int q = 0; q < a.x.world; ++q) t += __ldcv(data + (long long)q * a.x.cap + e);
+      a.fin_local[e] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *a.x.seq = seq;
+  }
   const int it = *a.it;
   const double* ft = a.fin_train;
   const double* sc = ft + (size_t)a.H * a.ctot;

@@ -112,6 +112,18 @@ class Engine:
         buf = (C.c_char * 128).from_buffer_copy(box[0])
         check(self.lib.rfb_engine_comm_init(self.handle, buf, rank, world))
         self.rank, self.world = rank, world
+        # one-shot NVLink exchange buffers (CUDA IPC); if the mapping fails the engine keeps NCCL
+        if world <= 8 and os.environ.get("RFB_XCHG", "1") != "0":
+            h = (C.c_char * 64)()
+            check(self.lib.rfb_engine_xchg_create(self.handle, h))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(h))
+            blob = (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles))
+            rc = self.lib.rfb_engine_xchg_connect(self.handle, blob)
+            ok = [None] * world
+            dist.all_gather_object(ok, int(rc))
+            if any(r != 0 for r in ok):          # all ranks must agree on the path they take
+                self.set_option("xchg", 0)
         return self
 
     def allreduce_f64(self, values):

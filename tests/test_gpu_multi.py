@@ -19,15 +19,17 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_sharded_fit_matches_single_gpu(world, tmp_path):
+@pytest.mark.parametrize("world,xchg", [(2, 1), (2, 0), (4, 1), (8, 1)])
+def test_sharded_fit_matches_single_gpu(world, xchg, tmp_path):
+    """xchg=1: gradient exchange by the fused one-shot NVLink kernel; xchg=0: NCCL all-reduce."""
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     out = tmp_path / "dist.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "dist_fit_worker.py"), str(out)]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, RFB_XCHG=str(xchg))
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     got = np.load(out)
 
