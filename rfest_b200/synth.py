@@ -56,6 +56,19 @@ class TensorRows:
         return self.data[a:b]
 
 
+class RowWindow:
+    """Rows [row0, row0 + n) of another row source as a recording of its own (train/dev splits)."""
+
+    def __init__(self, source, row0, n):
+        self.source, self.row0 = source, int(row0)
+        self.shape = (int(n),) + tuple(source.shape[1:])
+        self.chunk_rows = getattr(source, "chunk_rows", 1 << 18)
+        self.n_pix = getattr(source, "n_pix", None)
+
+    def rows(self, lo, hi):
+        return self.source.rows(self.row0 + lo, self.row0 + hi)
+
+
 def separable_filter(dims):
     """Ground-truth receptive field: biphasic temporal profile x Gaussian bump(s), unit norm
     (in the spirit of `gaussian3d`, rfest/simulate.py:19-22).  -> (kt [nlag], ks [n_pix] or None)."""
@@ -73,11 +86,20 @@ def separable_filter(dims):
     return kt.astype(np.float32), ks.astype(np.float32)
 
 
+def gaussian_response(engine, stim, dims, row_lo, row_hi, noise=0.1, seed=2046):
+    """y[t] = x_t . w + N(0, (noise * std)^2)  (`get_response(distr='gaussian')`, rfest/simulate.py:315-316)."""
+    return _response(engine, stim, dims, row_lo, row_hi, "gaussian", 1.0, 0.0, noise, seed)
+
+
 def poisson_response(engine, stim, dims, row_lo, row_hi, gain=1.5, rate=0.3, seed=2046):
     """y[t] ~ Poisson(softplus(gain * (x_t . w) + c)) for raw rows [row_lo, row_hi), computed on
     the device with the engine's own projection kernel (w = kt x ks is rank one, so the drive
     is a one-column 'basis').  Whole generation blocks are drawn so that the spikes of a row
     do not depend on which rank asks for it.  -> CUDA float32 tensor of length row_hi - row_lo."""
+    return _response(engine, stim, dims, row_lo, row_hi, "poisson", gain, rate, 0.0, seed)
+
+
+def _response(engine, stim, dims, row_lo, row_hi, kind, gain, rate, noise, seed):
     import torch
 
     from .engine import Block
@@ -101,11 +123,17 @@ def poisson_response(engine, stim, dims, row_lo, row_hi, gain=1.5, rate=0.3, see
     out = torch.empty(n, device=dev, dtype=torch.float32)
     engine.synchronize()
     flat = drive.as_torch()               # zero-copy view [n x 1] of the block (row stride 4)
-    u = gain * flat[:, 0] + float(np.log(np.expm1(rate)))
-    lam = torch.nn.functional.softplus(u)
+    if kind == "poisson":
+        u = gain * flat[:, 0] + float(np.log(np.expm1(rate)))
+        lam = torch.nn.functional.softplus(u)
+    else:
+        lam = flat[:, 0].clone()        # unit-norm filter on N(0,1) frames: std of the drive is 1
     for j in range(b_lo // BLOCK, (b_hi - 1) // BLOCK + 1):
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed * 7919 + 13 + j)
         a, b = j * BLOCK - b_lo, min((j + 1) * BLOCK, b_hi) - b_lo
-        out[a:b] = torch.poisson(lam[a:b], generator=gen)
+        if kind == "poisson":
+            out[a:b] = torch.poisson(lam[a:b], generator=gen)
+        else:
+            out[a:b] = lam[a:b] + noise * torch.randn(b - a, generator=gen, device=dev)
     return out[row_lo - b_lo: row_hi - b_lo].contiguous()

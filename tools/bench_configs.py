@@ -1,0 +1,103 @@
+"""The other BASELINE.json configurations on one GPU (parity-test shapes; not the bench line).
+
+    python tools/bench_configs.py 1 2 4 5        -> one JSON line per configuration
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rfest_b200 import GLM
+from rfest_b200.engine import Engine
+from rfest_b200.synth import GaussianStimulus, RowWindow, TensorRows, gaussian_response, poisson_response
+
+CONFIGS = {
+    1: dict(name="config 1: 1-D LNP dims [25] df [8] + history [20]/[8], 20k samples, 80/20 train/dev",
+            dims=[25], df=[8], n_raw=20000, distr="poisson", out="softplus", filt="none", subunits=1,
+            history=True, dev=0.2, alpha=1.0, beta=0.01, step=0.1, iters=1000),
+    2: dict(name="config 2: 3-D LNP dims [25,20,15] df [8,6,6] + history, 2^22 samples",
+            dims=[25, 20, 15], df=[8, 6, 6], n_raw=1 << 22, distr="poisson", out="softplus", filt="none",
+            subunits=1, history=True, dev=0.0, alpha=1.0, beta=0.01, step=0.01, iters=60),
+    4: dict(name="config 4: LNLN 4 subunits softplus/softplus, elastic net 0.5/0.01, 2^24 samples, 80/20 train/dev",
+            dims=[25, 20, 15], df=[8, 6, 6], n_raw=1 << 24, distr="poisson", out="softplus", filt="softplus",
+            subunits=4, history=True, dev=0.2, alpha=0.5, beta=0.01, step=0.01, iters=40),
+    5: dict(name="config 5: LG dims [40,32,32] df [12,10,10] (1200 coefficients), 2^24 samples",
+            dims=[40, 32, 32], df=[12, 10, 10], n_raw=1 << 24, distr="gaussian", out="none", filt="none",
+            subunits=1, history=False, dev=0.0, alpha=1.0, beta=0.001, step=0.01, iters=30),
+}
+
+
+def run(cid):
+    c = CONFIGS[cid]
+    eng = Engine.get(0)
+    dims, n_raw = c["dims"], c["n_raw"]
+    burn = dims[0] - 1
+    t0 = time.perf_counter()
+    stim = GaussianStimulus(n_raw, dims[1:], seed=2046, device=0)
+    resp = poisson_response if c["distr"] == "poisson" else gaussian_response
+    y = resp(eng, stim, dims, 0, n_raw)
+    n_tr = int(round(n_raw * (1 - c["dev"])))
+    parts = {"train": (0, n_tr)}
+    if c["dev"] > 0:
+        parts["dev"] = (n_tr, n_raw)
+    m = GLM(distr=c["distr"], output_nonlinearity=c["out"], device=0)
+    for kind, (a, b) in parts.items():
+        kw = dict(dims=dims, df=c["df"], smooth="cr", filter_nonlinearity=c["filt"]) if kind == "train" else {}
+        m.add_design_matrix(RowWindow(stim, a, b - a), name="stimulus", kind=kind, **kw)
+        if c["history"]:
+            kw = dict(dims=[20], df=[8], smooth="cr", shift=1) if kind == "train" else {}
+            m.add_design_matrix(TensorRows(y[a:b], 0, b - a), name="history", kind=kind, **kw)
+    m.initialize(num_subunits=c["subunits"], method="random", random_seed=2046)
+    for i, name in enumerate(m.filter_names):
+        m.p0[name] = (0.1 * np.random.default_rng(2046 + i).standard_normal(m.p0[name].shape)).astype(np.float32)
+    eng.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    m.alpha, m.beta, m.metric = c["alpha"], c["beta"], "corrcoef"
+    for kind, (a, b) in parts.items():
+        m.y[kind] = y[a + burn:b].cpu().numpy()
+    m._dirty = True
+    m._sync()
+    dm = m._dm
+    dm.set_params(*m._flatten(m.p0))
+    K, W = c["iters"], 3
+    dm.fit_begin(np.full(W + 2 * K, c["step"]), c["alpha"], c["beta"], "corrcoef")
+    ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda:0"))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dm.fit_run(W)
+    eng.synchronize()
+    ev0.record(ext)
+    dm.fit_run(K)
+    ev1.record(ext)
+    eng.synchronize()
+    ms = ev0.elapsed_time(ev1) / K
+    ms4 = dm.fit_run_timed(K)
+    dm.fit_finish(W + 2 * K - 1)
+    tr = dm.fit_traces(W + 2 * K)
+    dm.fit_end()
+    n_train = n_tr - burn
+    n_dev = (n_raw - n_tr - burn) if c["dev"] > 0 else 0
+    C = int(np.prod(c["df"])) + (8 if c["history"] else 0)
+    b_iter = 4.0 * (n_train + n_dev) * (C + 1)
+    out = {"config": c["name"], "iterations_per_s": 1e3 / ms, "ms_per_iter": ms,
+           "kernel_ms": {"train_sweep": ms4[0], "dev_sweep": ms4[1], "reduce": ms4[2], "update": ms4[3]},
+           "algorithmic_GB_per_iter": b_iter / 1e9,
+           "achieved_GBps_whole_iteration": b_iter / ms / 1e6,
+           "achieved_GBps_train_sweep": 4.0 * n_train * (C + 1) / ms4[0] / 1e6,
+           "frac_of_measured_6551": b_iter / ms / 1e6 / 6551, "setup_s": setup_s,
+           "loss_first_last": [float(tr[0][0]), float(tr[0][-1])]}
+    print(json.dumps(out), flush=True)
+    del m, dm, stim, y
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    for cid in [int(a) for a in sys.argv[1:]] or [1, 2, 4, 5]:
+        run(cid)
