@@ -39,6 +39,7 @@ struct SweepArgs {
   const float* head_icpt;           // [H]
   const float* glob_icpt;           // [1]
   int head_nl[kMaxHeads];
+  unsigned head_slotmask[kMaxHeads];  // bit i: head has columns among chunks [32 i, 32 i + 32)
   int out_nl;
   int distr;
   float two_over_n;                 // gaussian: 2 / n_global

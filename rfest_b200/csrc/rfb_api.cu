@@ -193,6 +193,7 @@ struct Plan {
   int n_chunks = 0, ctot = 0, NE = 0;
   std::vector<int> head_of;    // [F]
   std::vector<int> head_nl;    // [Ht]
+  std::vector<unsigned> head_slotmask;  // [Ht] chunk slots (of 32 chunks) each head has columns in
   std::vector<int> entry_of;   // [P]
   std::vector<int> coef0;      // [F] offset of the filter's coefficients in b
 };
@@ -277,7 +278,7 @@ static SweepFn sweep_instance(int Ht, int NCH, bool bwd, bool staged, int spec, 
   INST(1, 1, 8) INST(1, 3, 8) INST(1, 5, 4) INST(1, 10, 2)
   INST(2, 1, 8) INST(2, 3, 8) INST(2, 5, 4) INST(2, 10, 1)
   INST(3, 1, 8) INST(3, 3, 4) INST(3, 5, 2)
-  INST(5, 1, 8) INST(5, 3, 4)
+  INST(5, 1, 4) INST(5, 3, 4)
 #undef INST
   return nullptr;
 }
@@ -341,8 +342,11 @@ static int build_plan(rfb_model* m) {
     p.P += m->filters[f].n_coef;
   }
   p.entry_of.resize(p.P);
+  p.head_slotmask.assign(p.Ht, 0u);
   for (int f = 0; f < p.F; ++f) {
     const Filter& fl = m->filters[f];
+    const int c_lo = p.slot_chunk0[fl.slot], c_hi = c_lo + (fl.n_coef + 3) / 4;   // chunks this filter reads
+    for (int c = c_lo; c < c_hi; ++c) p.head_slotmask[p.head_of[f]] |= 1u << (c / 32);
     if (fl.n_coef > m->slot_cols[fl.slot])
       return fail(RFB_ERR_INVALID, "filter %d has %d coefficients but its block has %d columns", f,
                   fl.n_coef, m->slot_cols[fl.slot]);
@@ -530,7 +534,10 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   a.W = ps.W;
   a.head_icpt = ps.head_icpt;
   a.glob_icpt = ps.glob_icpt;
-  for (int h = 0; h < kMaxHeads; ++h) a.head_nl[h] = h < p.Ht ? head_nl[h] : RFB_NL_NONE;
+  for (int h = 0; h < kMaxHeads; ++h) {
+    a.head_nl[h] = h < p.Ht ? head_nl[h] : RFB_NL_NONE;
+    a.head_slotmask[h] = h < p.Ht ? p.head_slotmask[h] : 0u;
+  }
   a.out_nl = m->out_nl;
   a.distr = m->distr;
   a.two_over_n = ds.n_total > 0 ? (float)(2.0 / ds.n_total) : 0.f;

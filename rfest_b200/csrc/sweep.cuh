@@ -199,6 +199,56 @@ __device__ __forceinline__ void row_epilogue(const SweepArgs& a, const float (&t
   r_out = r;
 }
 
+// ---- multi-head epilogue (staged kernel, H > 1) --------------------------------------------------
+// After the transposed reduction lane L holds the dot product of (head, row) = (L / RB, L % RB)
+// (VP = next power of two >= H * RB lanes; the rest idle).  Every lane evaluates ONE filter
+// nonlinearity -- all H * RB of them in parallel instead of H in a row -- the per-row sums over
+// heads are three shuffles, the output nonlinearity / loss / delta are replicated per row.
+// Fills delta_hr (this lane's dL/da_{h,r}), and accumulates the row scalars in lanes < RB and
+// the head-intercept gradient of this lane's head in `sc_head`.
+template <int H, int RB, int VP>
+__device__ __forceinline__ void multihead_epilogue(const SweepArgs& a, float tot, float hic_lane, int kind_lane,
+                                                   bool lane_valid, float gic, bool poisson, float yv,
+                                                   bool rowok, int lane, float& delta_hr, float& r_out,
+                                                   float (&sc)[kNumScalars], float& sc_head) {
+  float f, dphi;
+  nl_eval(kind_lane, tot + hic_lane, f, dphi);
+  float u = lane_valid ? f : 0.f;
+#pragma unroll
+  for (int m = RB; m < VP; m <<= 1) u += __shfl_xor_sync(0xffffffffu, u, m);
+  u += gic;
+  float r, dr;
+  nl_eval(a.out_nl, u, r, dr);
+  float la, lb, dldr;
+  const float err = yv - r;
+  if (poisson) {                                   // rfest/loss.py:4-11
+    const bool fin = r != CUDART_INF_F;
+    const float r1 = fin ? r : 0.f;
+    const bool live = fin && (r1 > 1e-20f);
+    const float r2 = (r1 != r1) ? r1 : fmaxf(r1, 1e-20f);
+    la = -logf(r2) * yv;
+    lb = r2;
+    dldr = live ? (1.0f - fast_div(yv, r2)) : 0.f;
+  } else {                                         // rfest/loss.py:14-16
+    la = err * err;
+    lb = 0.f;
+    dldr = -err * a.two_over_n;
+  }
+  const float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
+  if (rowok && lane < RB) {
+    sc[S_LOSS_A] += la;
+    sc[S_LOSS_B] += lb;
+    sc[S_R] += r;
+    sc[S_RR] += r * r;
+    sc[S_YR] += yv * r;
+    sc[S_SQERR] += err * err;
+    sc[S_GGLOBAL] += delta;
+  }
+  delta_hr = (delta == 0.f || !lane_valid) ? 0.f : delta * dphi;
+  if (lane < H * RB) sc_head += delta_hr;
+  r_out = r;
+}
+
 // fp32 partials -> this warp's fp64 accumulator row (L2 resident).  The row was zeroed at kernel
 // start, so this is always read-modify-write.  Scalars live in lanes < RB only.
 template <int H, int NCH, int RB, bool BWD>
@@ -229,6 +279,16 @@ __device__ __forceinline__ void flush_partials(double* my_acc, int ctot, int lan
     if (lane == 0) my_acc[(size_t)H * ctot + k] += v;
     sc[k] = 0.f;
   }
+}
+
+// head-intercept gradients of the multi-head epilogue: lane L carries head L / RB
+template <int H, int RB>
+__device__ __forceinline__ void flush_head_scalar(double* my_acc, int ctot, int lane, float& sc_head) {
+  double v = (double)sc_head;
+#pragma unroll
+  for (int m = RB / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  if (lane < H * RB && (lane & (RB - 1)) == 0) my_acc[(size_t)H * ctot + S_GHEAD + lane / RB] += v;
+  sc_head = 0.f;
 }
 
 template <int H, int NCH, bool BWD>
@@ -511,7 +571,23 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
   for (int s = 0; s < NS; ++s)
     if (gw + (long long)s * GW < ntiles) issue(gw + (long long)s * GW, wbase + s * stage_bytes, bbase + 8u * s);
 
-  const int myr = lane & (RB - 1);
+  // multi-head layout: lane L <-> (head, row) = (L / RB, L % RB) among the first VP lanes
+  constexpr int V = H * RB;
+  constexpr int VP = V <= 1 ? 1 : V <= 2 ? 2 : V <= 4 ? 4 : V <= 8 ? 8 : V <= 16 ? 16 : 32;
+  static_assert(V <= 32, "H * RB must not exceed the warp size");
+  const int my_idx = lane & (VP - 1);
+  const bool lane_valid = my_idx < V;
+  const int my_h = lane_valid ? my_idx / RB : 0;
+  const float hic_lane = a.head_icpt[my_h];
+  const int kind_lane = lane_valid ? a.head_nl[my_h] : RFB_NL_NONE;
+  float sc_head = 0.f;
+  bool use[H][NCH];
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) use[h][i] = (H == 1) || ((a.head_slotmask[h] >> i) & 1u);
+
+  const int myr = (H == 1) ? (lane & (RB - 1)) : (my_idx % RB);
   int since_flush = 0;
   int buf = 0;
   uint32_t phase = 0;
@@ -536,24 +612,29 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
       else if (tile * RB + myr < a.n_rows) yv = __ldg(a.y + tile * RB + myr);
     }
 
-    float tot[H];
+    // forward: per (head, row) partial dot products (chunk slots a head has no columns in are
+    // skipped warp-uniformly), then ONE transposed reduction over all H * RB values
+    float pv[VP];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      float p[RB];
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
-          acc = fmaf(x[r][i].x, w[h][i].x, acc);
-          acc = fmaf(x[r][i].y, w[h][i].y, acc);
-          acc = fmaf(x[r][i].z, w[h][i].z, acc);
-          acc = fmaf(x[r][i].w, w[h][i].w, acc);
+          if (use[h][i]) {
+            acc = fmaf(x[r][i].x, w[h][i].x, acc);
+            acc = fmaf(x[r][i].y, w[h][i].y, acc);
+            acc = fmaf(x[r][i].z, w[h][i].z, acc);
+            acc = fmaf(x[r][i].w, w[h][i].w, acc);
+          }
         }
-        p[r] = acc;
+        pv[h * RB + r] = acc;
       }
-      tot[h] = transpose_reduce<RB>(p, lane);
     }
+#pragma unroll
+    for (int k = V; k < VP; ++k) pv[k] = 0.f;
+    const float tot_lane = transpose_reduce<VP>(pv, lane);
     // every lane's rows (and y) are in registers -- the dot products consumed them: hand the
     // buffer back to the copy engine for the tile NS ahead
     {
@@ -564,22 +645,45 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
 
     const long long myrow = tile * RB + myr;
     const bool rowok = myrow < a.n_rows;
-    const bool count = rowok && (lane < RB);
-    float dh[H], r;
-    row_epilogue<H, SPEC>(a, tot, hic, gic, poisson, rowok ? yv : 0.f, rowok, count, dh, r, sc);
-    if (a.r_out != nullptr && count) a.r_out[myrow] = r;
-    if (BWD) {
+    float r;
+    if constexpr (H == 1) {
+      const bool count = rowok && (lane < RB);
+      float tot[1] = {tot_lane}, dh[1];
+      row_epilogue<1, SPEC>(a, tot, hic, gic, poisson, rowok ? yv : 0.f, rowok, count, dh, r, sc);
+      if (a.r_out != nullptr && count) a.r_out[myrow] = r;
+      if (BWD) {
 #pragma unroll
-      for (int rr = 0; rr < RB; ++rr) {
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-          const float d = __shfl_sync(0xffffffffu, dh[h], rr);
+        for (int rr = 0; rr < RB; ++rr) {
+          const float d = __shfl_sync(0xffffffffu, dh[0], rr);
 #pragma unroll
           for (int i = 0; i < NCH; ++i) {
-            g[h][i].x = fmaf(d, x[rr][i].x, g[h][i].x);
-            g[h][i].y = fmaf(d, x[rr][i].y, g[h][i].y);
-            g[h][i].z = fmaf(d, x[rr][i].z, g[h][i].z);
-            g[h][i].w = fmaf(d, x[rr][i].w, g[h][i].w);
+            g[0][i].x = fmaf(d, x[rr][i].x, g[0][i].x);
+            g[0][i].y = fmaf(d, x[rr][i].y, g[0][i].y);
+            g[0][i].z = fmaf(d, x[rr][i].z, g[0][i].z);
+            g[0][i].w = fmaf(d, x[rr][i].w, g[0][i].w);
+          }
+        }
+      }
+    } else {
+      float delta_hr;
+      multihead_epilogue<H, RB, VP>(a, tot_lane, hic_lane, kind_lane, lane_valid, gic, poisson,
+                                    rowok ? yv : 0.f, rowok, lane, delta_hr, r, sc, sc_head);
+      if (a.r_out != nullptr && rowok && lane < RB) a.r_out[myrow] = r;
+      if (BWD) {
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) {
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const float d = __shfl_sync(0xffffffffu, delta_hr, h * RB + rr);
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+              if (use[h][i]) {
+                g[h][i].x = fmaf(d, x[rr][i].x, g[h][i].x);
+                g[h][i].y = fmaf(d, x[rr][i].y, g[h][i].y);
+                g[h][i].z = fmaf(d, x[rr][i].z, g[h][i].z);
+                g[h][i].w = fmaf(d, x[rr][i].w, g[h][i].w);
+              }
+            }
           }
         }
       }
@@ -590,10 +694,12 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
     }
     if (++since_flush >= a.flush_tiles) {
       flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+      if constexpr (H > 1) flush_head_scalar<H, RB>(my_acc, ctot, lane, sc_head);
       since_flush = 0;
     }
   }
   flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+  if constexpr (H > 1) flush_head_scalar<H, RB>(my_acc, ctot, lane, sc_head);
   cta_reduce<H, NCH, BWD>(a, ctot, NE);
 }
 
