@@ -123,7 +123,8 @@ struct rfb_engine {
   int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
   int sweep_stages = 0;   // depth of each warp's copy ring (0: sized for ~112 KB in flight per SM)
   int sweep_warps = 4;    // warps per CTA
-  int sweep_ctas = 1;     // CTAs per SM (0: as many as fit); 1 x 4 warps x 3 stages measured best on B200
+  int sweep_ctas = -1;    // CTAs per SM (0: as many as fit; -1: auto = 1 for single-head models, where
+                          // 4 warps x 3 stages measured best, as many as fit for the compute-heavier multi-head ones)
 };
 
 static int scratch_reserve(rfb_engine* e, Scratch& s, size_t bytes) {
@@ -457,7 +458,7 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
   if (stages <= 0) {
     // Measured on B200 (tools/tune_sweep.py, 2^25 x 296): bandwidth peaks with ~112 KB of rows in
     // flight per SM (4 warps x 3 stages x 9.5 KB); both fewer and more bytes in flight are slower.
-    const int ctas = e->sweep_ctas > 0 ? e->sweep_ctas : 1;
+    const int ctas = e->sweep_ctas > 0 ? e->sweep_ctas : (p.Ht == 1 ? 1 : 2);
     const double per_stage = (double)warps * ctas * sweep_stage_bytes(p.RB, p.ctot);
     stages = (int)std::lround(114688.0 / per_stage);
     stages = std::min(std::max(stages, 2), 8);
@@ -490,7 +491,8 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
     if (staged) { staged = 0; continue; }                   // rows too wide to stage: stream directly
     return fail(RFB_ERR_CUDA, "sweep kernel does not fit on an SM");
   }
-  if (e->sweep_ctas > 0) occ = std::min(occ, e->sweep_ctas);
+  const int want_ctas = e->sweep_ctas >= 0 ? e->sweep_ctas : (p.Ht == 1 ? 1 : 0);
+  if (want_ctas > 0) occ = std::min(occ, want_ctas);
   const int64_t ntiles = (ds.n + RB - 1) / RB;
   int64_t grid = (int64_t)e->num_sms * occ;
   const int64_t need = (ntiles + warps - 1) / warps;
