@@ -173,6 +173,11 @@ int rfb_model_n_params(rfb_model* m, int* n_coef_total, int* n_intercepts);
 int rfb_model_eval(rfb_model* m, int kind, const float* b, const double* intercepts,
                    float* r_out, double* sums);
 
+/* value_and_grad(cost) of the data term (_glm.py:692-696 without the penalty): the same sums plus
+ * d loss / d b [n_coef_total] and d loss / d intercepts [n_intercepts] (filters, then global), float64. */
+int rfb_model_value_and_grad(rfb_model* m, int kind, const float* b, const double* intercepts,
+                             double* sums, double* grad_b, double* grad_icpt);
+
 /* Normal-equation pieces for the least-squares initialisation (compute_mle, _glm.py:438-537):
  * over the concatenated, padded design columns of data set `kind` (ctot of them, slot after slot),
  * gram = XS^T XS [ctot x ctot], colsum = XS^T 1 [ctot], xty = XS^T y [ctot], all float64 and

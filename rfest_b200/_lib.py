@@ -66,6 +66,7 @@ SIGNATURES = {
     "rfb_model_get_params": (_i, [_p, _p, _p]),
     "rfb_model_n_params": (_i, [_p, _ip, _ip]),
     "rfb_model_eval": (_i, [_p, _i, _p, _p, _p, _p]),
+    "rfb_model_value_and_grad": (_i, [_p, _i, _p, _p, _p, _p, _p]),
     "rfb_model_gram": (_i, [_p, _i, _p, _p, _p, _ip]),
     "rfb_fit_begin": (_i, [_p, _i, _p, _d, _d, _i]),
     "rfb_fit_run": (_i, [_p, _i]),

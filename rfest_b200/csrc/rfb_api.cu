@@ -1264,8 +1264,8 @@ extern "C" int rfb_model_get_params(rfb_model* m, float* b, double* intercepts) 
   return RFB_OK;
 }
 
-extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const double* intercepts,
-                              float* r_out, double* sums) {
+static int eval_impl(rfb_model* m, int kind, const float* b, const double* intercepts, float* r_out,
+                     double* sums, double* grad_b, double* grad_ic) {
   if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
   if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
   DataSet& ds = m->data[kind];
@@ -1312,11 +1312,22 @@ extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const doub
     if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * ((size_t)ds.n + 4)));
     d_r = ds.r_buf;
   }
-  TRY(launch_sweep(m, kind, m->tmp, head_nl.data(), false, d_r));
-  // only the scalar tail matters for a forward pass
-  double* d_sc = m->fin_eval;
-  TRY(launch_reduce(m, kind, p.Ht * p.ctot, kNumScalars, d_sc, -1, 0, 0, nullptr));
-  TRY(allreduce_device_f64(e, d_sc, kNumScalars));
+  const bool want_grad = grad_b != nullptr || grad_ic != nullptr;
+  if (want_grad && !ds.has_y) return fail(RFB_ERR_STATE, "a gradient needs the response of kind %d", kind);
+  TRY(launch_sweep(m, kind, m->tmp, head_nl.data(), want_grad, d_r));
+  const int tail = p.Ht * p.ctot;
+  double* d_sc = m->fin_eval + (want_grad ? tail : 0);
+  std::vector<double> fin;
+  if (want_grad) {
+    TRY(launch_reduce(m, kind, 0, p.NE, m->fin_eval, -1, 0, 0, nullptr));
+    TRY(allreduce_device_f64(e, m->fin_eval, p.NE));
+    fin.resize(p.NE);
+    CU(cudaMemcpyAsync(fin.data(), m->fin_eval, sizeof(double) * p.NE, cudaMemcpyDeviceToHost, e->stream));
+  } else {
+    // only the scalar tail matters for a forward pass
+    TRY(launch_reduce(m, kind, tail, kNumScalars, d_sc, -1, 0, 0, nullptr));
+    TRY(allreduce_device_f64(e, d_sc, kNumScalars));
+  }
   double sc[kNumScalars];
   CU(cudaMemcpyAsync(sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, e->stream));
   if (r_out) CU(cudaMemcpyAsync(r_out, d_r, sizeof(float) * (size_t)ds.n, cudaMemcpyDeviceToHost, e->stream));
@@ -1331,7 +1342,24 @@ extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const doub
     sums[RFB_SUM_Y] = ds.sy;
     sums[RFB_SUM_YY] = ds.syy;
   }
+  if (grad_b)
+    for (int j = 0; j < p.P; ++j) grad_b[j] = fin[p.entry_of[j]];
+  if (grad_ic) {
+    for (int f = 0; f < p.F; ++f) grad_ic[f] = fin[tail + S_GHEAD + p.head_of[f]];
+    grad_ic[p.F] = fin[tail + S_GGLOBAL];
+  }
   return RFB_OK;
+}
+
+extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const double* intercepts,
+                              float* r_out, double* sums) {
+  return eval_impl(m, kind, b, intercepts, r_out, sums, nullptr, nullptr);
+}
+
+extern "C" int rfb_model_value_and_grad(rfb_model* m, int kind, const float* b, const double* intercepts,
+                                        double* sums, double* grad_b, double* grad_icpt) {
+  if (!grad_b || !grad_icpt) return fail(RFB_ERR_INVALID, "NULL gradient buffer");
+  return eval_impl(m, kind, b, intercepts, nullptr, sums, grad_b, grad_icpt);
 }
 
 extern "C" int rfb_model_gram(rfb_model* m, int kind, double* gram, double* colsum, double* xty, int* ctot_out) {

@@ -305,6 +305,18 @@ class DeviceModel:
             sums.ctypes.data_as(C.c_void_p)))
         return r, sums
 
+    def value_and_grad(self, kind, b, icpt):
+        """-> (sums, d loss/d b, d loss/d intercepts) of the data term at (b, icpt)."""
+        P, K = self.n_params()
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        icpt = np.ascontiguousarray(icpt, dtype=np.float64)
+        sums = np.zeros(_lib.N_SUMS, dtype=np.float64)
+        gb, gi = np.empty(P, dtype=np.float64), np.empty(K, dtype=np.float64)
+        check(self.lib.rfb_model_value_and_grad(
+            self.handle, _lib.KIND[kind], b.ctypes.data_as(C.c_void_p), icpt.ctypes.data_as(C.c_void_p),
+            sums.ctypes.data_as(C.c_void_p), gb.ctypes.data_as(C.c_void_p), gi.ctypes.data_as(C.c_void_p)))
+        return sums, gb, gi
+
     def gram(self, kind):
         """-> (G [ctot x ctot], colsum [ctot], xty [ctot]) in float64 over the padded, concatenated
         design columns (slot after slot); see rfb_model_gram."""

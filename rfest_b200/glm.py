@@ -572,6 +572,32 @@ class GLM:
                                                          + np.float32(self.alpha) * l1))
         return np.float64(loss)
 
+    def value_and_grad(self, p, kind="train", penalize=True):
+        """`value_and_grad(self.cost)(p)` (_glm.py:692-696) in one sweep: -> (cost, gradient dict with
+        the layout of `p`).  Extension of the reference surface (there it is a local of `optimize`)."""
+        self._sync()
+        b, ic = self._flatten(p)
+        sums, gb, gi = self._dm.value_and_grad(kind, b, ic)
+        loss = self._loss_from_sums(sums, kind)
+        gb = gb.astype(np.float64)
+        if penalize and (self.beta is not None and self.beta != 0) and kind == "train":
+            w = b.astype(np.float64)
+            if self.alpha != 0.0:
+                loss += self.beta * self.alpha * np.sum(np.abs(w))
+                gb = gb + self.beta * self.alpha * np.sign(w)
+            if self.alpha != 1.0:
+                nrm = np.sqrt(np.sum(w * w))
+                loss += self.beta * (1.0 - self.alpha) * nrm
+                gb = gb + self.beta * (1.0 - self.alpha) * w / nrm
+        g, pos = {}, 0
+        for name in self.filter_names:
+            k = self.n_features[name]
+            g[name] = gb[pos:pos + k].reshape(k, 1)
+            pos += k
+        g["intercept"] = {name: float(gi[i]) for i, name in enumerate(self.filter_names)}
+        g["intercept"]["global"] = float(gi[len(self.filter_names)])
+        return np.float64(loss), g
+
     # ------------------------------------------------------------------------------------
     # optimisation
     # ------------------------------------------------------------------------------------

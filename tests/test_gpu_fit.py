@@ -402,3 +402,39 @@ def test_reference_recipe_history_filter():                # tests/test_glm.py:1
     assert model.score({"stimulus": dv[0], "history": dv[1]}, dv[1], metric="corrcoef") > 0.3
     assert model.score({"stimulus": te[0], "history": te[1]}, te[1], metric="corrcoef") > 0.2
     assert _mse_uvec(model.w["opt"]["stimulus"], w_true) < 0.01
+
+
+# ---- value_and_grad through the C ABI ---------------------------------------------------------------
+@pytest.mark.parametrize("distr,out_nl,filt_nl,subunits", [
+    ("poisson", "softplus", "none", 1), ("poisson", "exponential", "none", 1), ("gaussian", "none", "none", 1),
+    ("poisson", "softplus", "softplus", 3), ("gaussian", "none", "tanh", 2), ("poisson", "softplus", "sigmoid", 1),
+    ("gaussian", "relu", "leaky_relu", 1), ("poisson", "softplus", "softplus", 4)])
+def test_value_and_grad_matches_oracle(distr, out_nl, filt_nl, subunits):
+    n = 1501
+    stim, y, _ = helpers.lnp_data(n, (8, 5, 4), seed=13)
+    if distr == "gaussian":
+        y = (y - y.mean()).astype(np.float32)
+    g, o = _pair(distr, out_nl)
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity=filt_nl,
+                            name="stimulus")
+        m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(num_subunits=subunits, method="random", random_seed=3)
+        m.alpha, m.beta = 0.5, 0.01
+    _same_p0([o, g], scale=0.2, icpt=0.03)
+    # distinct subunits (the optimiser would keep identical ones identical)
+    for k, name in enumerate(o.filter_names):
+        bump = (0.05 * np.random.default_rng(900 + k).standard_normal(np.asarray(o.p0[name]).shape)).astype(np.float32)
+        o.p0[name] = o.p0[name] + bump
+        g.p0[name] = (g.p0[name] + bump).astype(np.float32)
+    for m in (g, o):
+        m.y["train"] = np.asarray(y)[m.burn_in:].astype(m.dtype)
+    g._dirty = True
+    lg, gg = g.value_and_grad(g.p0, "train")
+    lo, go = o.value_and_grad(o.p0, "train")
+    assert abs(lg - lo) < 1e-6 * abs(lo)
+    for name in o.filter_names:
+        scale = np.abs(go[name]).max()
+        assert np.abs(gg[name] - go[name]).max() < 2e-5 * scale
+        assert abs(gg["intercept"][name] - go["intercept"][name]) < 2e-5 * max(1.0, abs(go["intercept"][name]))
+    assert abs(gg["intercept"]["global"] - go["intercept"]["global"]) < 2e-5 * max(1.0, abs(go["intercept"]["global"]))
