@@ -11,18 +11,23 @@
 // go to their own accumulator, the hi.hi term is dealt round-robin over `n_acc` accumulators, and the
 // epilogue adds the partial sums with round-to-nearest fp32.
 //
-// Structure (one CTA per SM, persistent over 128-row tiles of A; 10 warps):
-//   warp 8      TMA producer: per 32-wide K tile one 2-D bulk-tensor copy of the raw A tile
-//               (128 x 32 fp32, SWIZZLE_128B) and of the pre-split B_hi / B_lo tiles (N x 32), all
-//               signalling the stage's mbarrier with their byte counts.
-//   warps 4-7   splitters: turn the landed raw A tile into A_hi (in place) and A_lo with
-//               conflict-free 16-byte LDS/STS (the split is element-wise, hence layout-agnostic),
-//               fence the generic->async proxy and hand the stage to the MMA warp.
-//   warps 0-3   epilogue: tcgen05.ld the partial 128 x N fp32 accumulators out of TMEM (lane = row),
-//               add them and store Z with 16-byte stores, while the next tile is already running.
-//   warp 9      MMA issuer: one elected thread issues 12 tcgen05.mma (4 k-steps x 3 products) per
-//               stage from shared-memory descriptors into one of two TMEM accumulator buffers,
-//               tcgen05.commit releases the stage / publishes the accumulator.
+// Structure (one CTA per SM, persistent over 128-row tiles of A; 11 warps):
+//   warp 8      A producer: per 32-wide K tile one 2-D TMA load (cp.async.bulk.tensor.2d,
+//               SWIZZLE_128B) of the raw 128 x 32 fp32 A tile into a deep ring of raw slots -- this ring
+//               is what keeps enough HBM bytes in flight.
+//   warp 10     B producer: TMA loads of the pre-split B_hi / B_lo tiles (N x 32, L2 resident) straight
+//               into the MMA ring.
+//   warps 4-7   splitters: read a landed raw slot, write A_hi = tf32(A) and A_lo = A - A_hi into the
+//               MMA ring with conflict-free 16-byte LDS/STS (the split is element-wise, hence
+//               layout-agnostic), fence the generic->async proxy, release the raw slot.
+//   warp 9      MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (4 k-steps x 3 products)
+//               per K tile from shared-memory descriptors into one of two TMEM accumulator sets;
+//               tcgen05.commit releases the MMA slot; every `drain` K tiles it publishes the set and
+//               switches to the other one.
+//   warps 0-3   accumulate + epilogue: tcgen05.ld the published partial sums (lane = row), add them
+//               into fp32 registers with round-to-nearest, and store the finished 128 x N tile of Z.
+// Keeping the TMEM accumulation chains short (4 * drain MMAs) is what holds fp32-level accuracy: the
+// tensor core adds into its accumulator with truncation (measured bias ~ -0.5 ulp per MMA).
 #pragma once
 
 #include <cuda.h>
@@ -33,26 +38,29 @@ namespace rfb {
 
 constexpr int kTcM = 128;     // rows of A per tile = TMEM lanes
 constexpr int kTcK = 32;      // K tile: 32 fp32 = 128 bytes = one swizzle atom
-constexpr int kTcThreads = 320;   // warps 0-3 epilogue (TMEM lanes), 4-7 splitters, 8 TMA, 9 MMA
+constexpr int kTcThreads = 352;   // warps 0-3 epilogue (TMEM lanes), 4-7 splitters, 8 A-TMA, 9 MMA, 10 B-TMA
+constexpr int kTcMaxN = 128;
 
 struct TcArgs {
   long long n_rows;   // M
   int n_k_tiles;      // ceil(K / 32)
   int n;              // real N (columns of Z)
   int n_pad;          // UMMA N (multiple of 16, <= 128)
-  int n_stages;
+  int n_stages;       // MMA ring slots (A_hi, A_lo, B_hi, B_lo)
   float* Z;           // [M x ldz]
   int ldz;
-  int tmem_cols;      // power of two >= n_bufs * (n_acc + 1) * n_pad
-  int n_acc;          // independent accumulators of the hi.hi product (round-robin over k-steps)
-  int n_bufs;         // 1 or 2 accumulator sets (2: the epilogue overlaps the next tile's MMAs)
+  int tmem_cols;      // power of two >= 4 * n_pad (two sets of {hi.hi, cross terms})
+  int drain;          // K tiles accumulated in TMEM before the partial sums move to registers
+  int n_raw;          // raw A slots
 };
 
+constexpr size_t kTcRawBytes = (size_t)kTcM * kTcK * sizeof(float);   // 16 KB
 __host__ __device__ inline size_t tc_stage_bytes(int n_pad) {
-  return (size_t)2 * kTcM * kTcK * sizeof(float) + (size_t)2 * n_pad * kTcK * sizeof(float);
+  return 2 * kTcRawBytes + (size_t)2 * n_pad * kTcK * sizeof(float);
 }
-__host__ __device__ inline size_t tc_smem_bytes(int n_pad, int stages) {
-  return 1024 /* alignment slack */ + (size_t)stages * tc_stage_bytes(n_pad) + 256 /* barriers */;
+__host__ __device__ inline size_t tc_smem_bytes(int n_pad, int stages, int n_raw) {
+  return 1024 /* alignment slack */ + (size_t)stages * tc_stage_bytes(n_pad) + (size_t)n_raw * kTcRawBytes +
+         512 /* barriers */;
 }
 
 namespace tc {
@@ -119,29 +127,37 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                           const __grid_constant__ CUtensorMap map_blo, const TcArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 1024-byte aligned stage area (SWIZZLE_128B atoms are 8 x 128 bytes)
+  // 1024-byte aligned tile area (SWIZZLE_128B atoms are 8 x 128 bytes)
   const uint32_t base = (tc::s32(tc_smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = kTcM * kTcK * sizeof(float);            // 16 KB
+  const uint32_t a_bytes = (uint32_t)kTcRawBytes;
   const uint32_t b_bytes = (uint32_t)a.n_pad * kTcK * sizeof(float);
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const int NS = a.n_stages;
+  const int NS = a.n_stages, NR = a.n_raw;
   auto st_ahi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
   auto st_alo = [&](int s) { return base + (uint32_t)s * stage_bytes + a_bytes; };
   auto st_bhi = [&](int s) { return base + (uint32_t)s * stage_bytes + 2 * a_bytes; };
   auto st_blo = [&](int s) { return base + (uint32_t)s * stage_bytes + 2 * a_bytes + b_bytes; };
-  const uint32_t bars = base + (uint32_t)NS * stage_bytes;        // 8-byte mbarriers
-  auto bar_raw = [&](int s) { return bars + 8u * s; };              // TMA landed
-  auto bar_split = [&](int s) { return bars + 8u * (NS + s); };     // hi/lo ready
-  auto bar_empty = [&](int s) { return bars + 8u * (2 * NS + s); }; // MMAs done with the stage
-  auto bar_tfull = [&](int b) { return bars + 8u * (3 * NS + b); };     // accumulator complete
-  auto bar_tempty = [&](int b) { return bars + 8u * (3 * NS + 2 + b); }; // accumulator drained
-  const uint32_t tmem_slot = bars + 8u * (3 * NS + 4);
+  const uint32_t raw0 = base + (uint32_t)NS * stage_bytes;
+  auto st_raw = [&](int r) { return raw0 + (uint32_t)r * a_bytes; };
+  const uint32_t bars = raw0 + (uint32_t)NR * a_bytes;              // 8-byte mbarriers
+  auto bar_rfull = [&](int r) { return bars + 8u * r; };               // raw A landed            (tx)
+  auto bar_rempty = [&](int r) { return bars + 8u * (NR + r); };       // raw slot consumed       (128)
+  auto bar_split = [&](int s) { return bars + 8u * (2 * NR + s); };    // A_hi / A_lo written     (128)
+  auto bar_bfull = [&](int s) { return bars + 8u * (2 * NR + NS + s); };      // B tiles landed   (tx)
+  auto bar_mempty = [&](int s) { return bars + 8u * (2 * NR + 2 * NS + s); }; // MMAs read slot   (1)
+  auto bar_tfull = [&](int b) { return bars + 8u * (2 * NR + 3 * NS + b); };      // partial sums published (1)
+  auto bar_tempty = [&](int b) { return bars + 8u * (2 * NR + 3 * NS + 2 + b); }; // ... drained       (128)
+  const uint32_t tmem_slot = bars + 8u * (2 * NR + 3 * NS + 4);
 
   if (threadIdx.x == 0) {
+    for (int r = 0; r < NR; ++r) {
+      tc::mbar_init(bar_rfull(r), 1);
+      tc::mbar_init(bar_rempty(r), 128);
+    }
     for (int s = 0; s < NS; ++s) {
-      tc::mbar_init(bar_raw(s), 1);
       tc::mbar_init(bar_split(s), 128);
-      tc::mbar_init(bar_empty(s), 1);
+      tc::mbar_init(bar_bfull(s), 1);
+      tc::mbar_init(bar_mempty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(bar_tfull(b), 1);
@@ -164,18 +180,30 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
   const int KT = a.n_k_tiles;
 
   if (warp == 8) {
-    // ================= TMA producer =================
+    // ================= A producer (raw ring) =================
+    if (lane == 0) {
+      int r = 0;
+      uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kt = 0; kt < KT; ++kt) {
+          tc::mbar_wait(bar_rempty(r), ph ^ 1u);
+          tc::mbar_expect_tx(bar_rfull(r), a_bytes);
+          tc::tma_load_2d(st_raw(r), &map_a, kt * kTcK, (int)(tile * kTcM), bar_rfull(r));
+          if (++r == NR) { r = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ================= B producer (MMA ring) =================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t tx = a_bytes + 2 * b_bytes;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int kt = 0; kt < KT; ++kt) {
-          tc::mbar_wait(bar_empty(s), ph ^ 1u);
-          tc::mbar_expect_tx(bar_raw(s), tx);
-          tc::tma_load_2d(st_ahi(s), &map_a, kt * kTcK, (int)(tile * kTcM), bar_raw(s));
-          tc::tma_load_2d(st_bhi(s), &map_bhi, kt * kTcK, 0, bar_raw(s));
-          tc::tma_load_2d(st_blo(s), &map_blo, kt * kTcK, 0, bar_raw(s));
+          tc::mbar_wait(bar_mempty(s), ph ^ 1u);
+          tc::mbar_expect_tx(bar_bfull(s), 2 * b_bytes);
+          tc::tma_load_2d(st_bhi(s), &map_bhi, kt * kTcK, 0, bar_bfull(s));
+          tc::tma_load_2d(st_blo(s), &map_blo, kt * kTcK, 0, bar_bfull(s));
           if (++s == NS) { s = 0; ph ^= 1u; }
         }
       }
@@ -187,48 +215,52 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
       int s = 0, buf = 0;
       uint32_t ph = 0, tph = 0;
-      const uint32_t set_cols = (uint32_t)((a.n_acc + 1) * a.n_pad);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        tc::mbar_wait(bar_tempty(buf), tph ^ 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d0 = tmem_base + (uint32_t)buf * set_cols;
-        const uint32_t d_small = d0 + (uint32_t)(a.n_acc * a.n_pad);
-        uint32_t small_acc = 0;
-        int step = 0;
         for (int kt = 0; kt < KT; ++kt) {
+          const bool first = (kt % a.drain) == 0;          // first K tile into this accumulator set
+          if (first) {
+            tc::mbar_wait(bar_tempty(buf), tph ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t d_main = tmem_base + (uint32_t)(buf * 2 * a.n_pad);
+          const uint32_t d_small = d_main + (uint32_t)a.n_pad;
           tc::mbar_wait(bar_split(s), ph);
+          tc::mbar_wait(bar_bfull(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-          for (int ks = 0; ks < kTcK / 8; ++ks, ++step) {
+          for (int ks = 0; ks < kTcK / 8; ++ks) {
             const uint32_t off = (uint32_t)ks * 32u;   // 8 tf32 = 32 bytes along K inside the swizzle atom
             const uint64_t ahi = tc::smem_desc(st_ahi(s) + off), alo = tc::smem_desc(st_alo(s) + off);
             const uint64_t bhi = tc::smem_desc(st_bhi(s) + off), blo = tc::smem_desc(st_blo(s) + off);
-            tc::mma_tf32(d_small, alo, bhi, idesc, small_acc);
-            small_acc = 1;
+            const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+            tc::mma_tf32(d_small, alo, bhi, idesc, acc);
             tc::mma_tf32(d_small, ahi, blo, idesc, 1);
-            tc::mma_tf32(d0 + (uint32_t)((step % a.n_acc) * a.n_pad), ahi, bhi, idesc, step >= a.n_acc ? 1u : 0u);
+            tc::mma_tf32(d_main, ahi, bhi, idesc, acc);
           }
-          tc::commit(bar_empty(s));          // stage reusable once these MMAs have read it
+          tc::commit(bar_mempty(s));         // slot reusable once these MMAs have read it
           if (++s == NS) { s = 0; ph ^= 1u; }
+          if ((kt % a.drain) == a.drain - 1 || kt == KT - 1) {
+            tc::commit(bar_tfull(buf));      // partial sums complete
+            if (++buf == 2) { buf = 0; tph ^= 1u; }
+          }
         }
-        tc::commit(bar_tfull(buf));          // accumulators complete
-        if (++buf == a.n_bufs) { buf = 0; tph ^= 1u; }
       }
     }
   } else if (warp >= 4) {
     // ================= splitters (warps 4-7, 128 threads) =================
     const int t = threadIdx.x - 128;
-    int s = 0;
-    uint32_t ph = 0;
+    int s = 0, r = 0;
+    uint32_t ph = 0, rph = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kt = 0; kt < KT; ++kt) {
-        tc::mbar_wait(bar_raw(s), ph);
-        const uint32_t hi_base = st_ahi(s), lo_base = st_alo(s);
+        tc::mbar_wait(bar_rfull(r), rph);
+        tc::mbar_wait(bar_mempty(s), ph ^ 1u);
+        const uint32_t src = st_raw(r), hi_base = st_ahi(s), lo_base = st_alo(s);
 #pragma unroll
         for (int i = 0; i < (kTcM * kTcK / 4) / 128; ++i) {      // 1024 16-byte chunks / 128 threads
           const uint32_t off = (uint32_t)(t + 128 * i) * 16u;
           uint32_t x0, x1, x2, x3;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(hi_base + off));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(src + off));
           const uint32_t h0 = x0 & 0xFFFFE000u, h1 = x1 & 0xFFFFE000u, h2 = x2 & 0xFFFFE000u, h3 = x3 & 0xFFFFE000u;
           const float l0 = __uint_as_float(x0) - __uint_as_float(h0), l1 = __uint_as_float(x1) - __uint_as_float(h1);
           const float l2 = __uint_as_float(x2) - __uint_as_float(h2), l3 = __uint_as_float(x3) - __uint_as_float(h3);
@@ -237,52 +269,56 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
         tc::mbar_arrive(bar_split(s));
+        tc::mbar_arrive(bar_rempty(r));      // the raw slot may be refilled
         if (++s == NS) { s = 0; ph ^= 1u; }
+        if (++r == NR) { r = 0; rph ^= 1u; }
       }
     }
   } else {
-    // ================= epilogue (warps 0-3: thread = TMEM lane = row inside the tile) =================
+    // ================= accumulate + epilogue (warps 0-3: thread = TMEM lane = row of the tile) =========
     const int t = threadIdx.x;
     int buf = 0;
     uint32_t tph = 0;
     const bool vec_ok = (a.ldz % 4) == 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      tc::mbar_wait(bar_tfull(buf), tph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const long long row = tile * kTcM + t;
-      const uint32_t set_cols = (uint32_t)((a.n_acc + 1) * a.n_pad);
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * set_cols;
-      // every accumulator needs at least one k-step to be defined: n_acc <= 4 * KT is enforced on the host
-      for (int c0 = 0; c0 < a.n_pad; c0 += 16) {
-        uint32_t v[16];
-        float sum[16];
-        tc::tmem_ld16(taddr + (uint32_t)(a.n_acc * a.n_pad + c0), v);   // the small cross terms first
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float z[kTcMaxN];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(v[j]);
-        for (int k = 0; k < a.n_acc; ++k) {
-          tc::tmem_ld16(taddr + (uint32_t)(k * a.n_pad + c0), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < kTcMaxN; ++j) z[j] = 0.f;
+      for (int k0 = 0; k0 < KT; k0 += a.drain) {
+        tc::mbar_wait(bar_tfull(buf), tph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 2 * a.n_pad);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+        for (int c0 = 0; c0 < kTcMaxN; c0 += 16) {
+          if (c0 < a.n_pad) {
+            uint32_t v[16], u[16];
+            tc::tmem_ld16(taddr + (uint32_t)c0, v);                       // hi.hi partial
+            tc::tmem_ld16(taddr + (uint32_t)(a.n_pad + c0), u);            // cross terms
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+          }
         }
-        if (row < a.n_rows) {
-          float* zr = a.Z + row * a.ldz + c0;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc::mbar_arrive(bar_tempty(buf));
+        if (++buf == 2) { buf = 0; tph ^= 1u; }
+      }
+      const long long row = tile * kTcM + t;
+      if (row < a.n_rows) {
+        float* zr = a.Z + row * a.ldz;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            if (vec_ok && c0 + j + 3 < a.n) {
-              *reinterpret_cast<float4*>(zr + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+        for (int c = 0; c < kTcMaxN; c += 4) {
+          if (c < a.n) {
+            if (vec_ok && c + 3 < a.n) {
+              *reinterpret_cast<float4*>(zr + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
             } else {
 #pragma unroll
-              for (int jj = j; jj < j + 4; ++jj)
-                if (c0 + jj < a.n) zr[jj] = sum[jj];
+              for (int cc = c; cc < c + 4; ++cc)
+                if (cc < a.n) zr[cc] = z[cc];
             }
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      tc::mbar_arrive(bar_tempty(buf));
-      if (++buf == a.n_bufs) { buf = 0; tph ^= 1u; }
     }
   }
 

@@ -880,7 +880,7 @@ static bool make_map_2d(CUtensorMap* map, const float* ptr, uint64_t rows, uint6
 
 struct TcPlan {
   bool ok = false;
-  int n_pad = 0, k_tiles = 0, stages = 0, tmem_cols = 0, n_acc = 1, n_bufs = 1;
+  int n_pad = 0, k_tiles = 0, stages = 0, tmem_cols = 0, drain = 4, n_raw = 0;
   size_t smem = 0;
   const float *bhi = nullptr, *blo = nullptr;   // device, [n_pad x k_tiles*32], K contiguous
   CUtensorMap map_bhi, map_blo;
@@ -895,16 +895,18 @@ static int tc_prepare(rfb_engine* e, const float* Sxy, int n_pix, int n_q, TcPla
   tp->n_pad = (n_q + 15) / 16 * 16;
   tp->k_tiles = (n_pix + kTcK - 1) / kTcK;
   const int kpad = tp->k_tiles * kTcK;
-  // TMEM budget (512 columns): n_acc accumulators for the hi.hi term + one for the cross terms, twice
-  // if it fits (so that the epilogue overlaps the next tile)
-  tp->n_acc = std::min(4, 512 / tp->n_pad - 1);
-  tp->n_acc = std::max(1, std::min(tp->n_acc, tp->k_tiles * (kTcK / 8)));
-  tp->n_bufs = (2 * (tp->n_acc + 1) * tp->n_pad <= 512) ? 2 : 1;
+  // TMEM: two sets of {hi.hi, cross terms} accumulators; a set is drained into registers every
+  // `drain` K tiles so that no accumulation chain exceeds 4 * drain truncating adds
+  tp->drain = 4;
   tp->tmem_cols = 32;
-  while (tp->tmem_cols < tp->n_bufs * (tp->n_acc + 1) * tp->n_pad) tp->tmem_cols *= 2;
-  tp->stages = (int)std::min<size_t>(6, (200 * 1024) / tc_stage_bytes(tp->n_pad));
-  if (tp->stages < 2) return RFB_OK;
-  tp->smem = tc_smem_bytes(tp->n_pad, tp->stages);
+  while (tp->tmem_cols < 4 * tp->n_pad) tp->tmem_cols *= 2;
+  // shared memory: two MMA slots + as many raw A slots (HBM bytes in flight) as fit
+  tp->stages = 2;
+  const size_t budget = 225 * 1024;
+  const size_t fixed = 1024 + 512 + (size_t)tp->stages * tc_stage_bytes(tp->n_pad);
+  if (fixed + 2 * kTcRawBytes > budget) return RFB_OK;
+  tp->n_raw = (int)std::min<size_t>(8, (budget - fixed) / kTcRawBytes);
+  tp->smem = tc_smem_bytes(tp->n_pad, tp->stages, tp->n_raw);
   // hi = tf32 truncation of b, lo = b - hi (exact); transposed so that K is contiguous (K-major B)
   std::vector<float> h((size_t)2 * tp->n_pad * kpad, 0.f);
   float* hi = h.data();
@@ -951,8 +953,8 @@ static bool tc_launch(rfb_engine* e, const TcPlan& tp, const float* d_stim, int6
   a.Z = Z;
   a.ldz = n_q;
   a.tmem_cols = tp.tmem_cols;
-  a.n_acc = tp.n_acc;
-  a.n_bufs = tp.n_bufs;
+  a.drain = tp.drain;
+  a.n_raw = tp.n_raw;
   const int64_t tiles = (nz + kTcM - 1) / kTcM;
   const int grid = (int)std::min<int64_t>(tiles, e->num_sms);
   spatial_project_tc_kernel<<<grid, kTcThreads, tp.smem, e->stream>>>(map_a, tp.map_bhi, tp.map_blo, a);
