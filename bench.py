@@ -182,7 +182,7 @@ def gpu_arm(args):
     model = GLM(distr="poisson", output_nonlinearity="softplus", device=local_rank)
     model.add_design_matrix(stim, dims=DIMS, df=DF, smooth="cr", name="stimulus")
     model.add_design_matrix(y_rows, dims=H_DIMS, df=H_DF, smooth="cr", shift=1, name="history")
-    model.initialize(num_subunits=1, method="random", random_seed=2046)
+    model.initialize(num_subunits=1, method="random", random_seed=2046, compute_ci=False)
     for i, name in enumerate(model.filter_names):
         model.p0[name] = (0.1 * np.random.default_rng(2046 + i).standard_normal(
             model.p0[name].shape)).astype(np.float32)

@@ -184,6 +184,12 @@ int rfb_model_value_and_grad(rfb_model* m, int kind, const float* b, const doubl
  * all-reduced over ranks.  Any output may be NULL; with all three NULL only *ctot is set. */
 int rfb_model_gram(rfb_model* m, int kind, double* gram, double* colsum, double* xty, int* ctot);
 
+/* XS_f^T diag(U) XS_f [n_coef x n_coef] of one filter (float64, all-reduced), the matrix whose inverse
+ * is the coefficient covariance of _get_filter_variance (_glm.py:1058-1164): weighted = 0 gives the
+ * plain Gram (Gaussian case); weighted = 1 uses U = 1 / fnl(fnl(XS_f b_f, filter_nl), output_nl)^2 with
+ * `b` the full coefficient vector (no intercepts, as in the reference). */
+int rfb_model_filter_gram(rfb_model* m, int kind, int filter, const float* b, int weighted, double* gram);
+
 /* ---- fit loop (GLM.optimize, _glm.py:644-836) --------------------------------------------- */
 /* Prepare `max_iters` iterations from the current parameters with zeroed Adam state:
  *   step_sizes[max_iters]  per-iteration learning rate (a constant or a schedule evaluated

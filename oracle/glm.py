@@ -327,11 +327,12 @@ class OracleGLM:
 
     def initialize(self, y=None, num_subunits=1, dt=0.033, method="random", compute_ci=True,
                    random_seed=2046, verbose=0, add_noise_to_mle=False):
-        """_glm.py:395-436.  Confidence intervals are out of scope (compute_ci ignored)."""
+        """_glm.py:395-436.  `compute_ci` covers `_get_filter_variance`; the response bands
+        (`_get_response_variance`) are out of scope."""
         self.dt = dt
         self.init_method = method
         self.num_subunits = num_subunits
-        self.compute_ci = False
+        self.compute_ci = compute_ci
         if method == "random":
             self._initialize_random(random_seed=random_seed)
         elif method == "mle":
@@ -576,8 +577,45 @@ class OracleGLM:
                                       return_model, atol, min_iters)
         self._extract_opt_params()
 
+    def _get_filter_variance(self, w_type="opt"):
+        """_glm.py:1058-1164, spline and raw filters alike."""
+        self.V = getattr(self, "V", {})
+        self.b_se = getattr(self, "b_se", {})
+        self.w_se = getattr(self, "w_se", {})
+        V, b_se, w_se = {}, {}, {}
+        p = self.p[w_type]
+        if self.distr == "gaussian":
+            y = self.y["train"]
+            rss = np.sum((y - self.forwardpass(p, "train")) ** 2)                # :1068-1071
+        for name in self.filter_names:
+            M = (self.XS["train"][name] if name in self.S else self.X["train"][name]).astype(np.float64)
+            if self.distr == "gaussian":
+                G = M.T @ M
+                try:
+                    Vn = np.linalg.inv(G)
+                except np.linalg.LinAlgError:
+                    Vn = np.linalg.pinv(G)
+                Vn = Vn * (rss / (len(y) - sum(self.df[name])))                     # :1073,1088
+            else:
+                b = np.asarray(p[name], dtype=np.float64)
+                u = fnl((M @ b).ravel(), self.filter_nonlinearity[name])          # :1126-1128
+                U = 1 / fnl(u, self.output_nonlinearity) ** 2                      # :1129-1131
+                G = (M.T * U) @ M
+                try:
+                    Vn = np.linalg.inv(G)                                           # :1134
+                except np.linalg.LinAlgError:
+                    Vn = np.linalg.pinv(G)
+            V[name] = np.abs(Vn)
+            se = np.sqrt(np.diag(V[name]))
+            if name in self.S:
+                b_se[name] = se
+                w_se[name] = self.S[name] @ se
+            else:
+                w_se[name] = se
+        self.V[w_type], self.b_se[w_type], self.w_se[w_type] = V, b_se, w_se
+
     def _extract_opt_params(self):
-        """_glm.py:920-930 (confidence intervals out of scope)."""
+        """_glm.py:920-933."""
         self.b["opt"], self.w["opt"] = {}, {}
         for name in self.filter_names:
             if name in self.S:
@@ -586,6 +624,8 @@ class OracleGLM:
             else:
                 self.w["opt"][name] = self.p["opt"][name]
         self.intercept["opt"] = self.p["opt"]["intercept"]
+        if self.compute_ci:
+            self._get_filter_variance("opt")
 
     # ---- predict / score ---------------------------------------------------
     def predict(self, X, w_type="opt"):

@@ -22,14 +22,18 @@ struct GramArgs {
   int ctot;
   long long n_rows;
   const float* y;                 // may be nullptr
-  int n_tiles;                    // ceil(ctot / 64)
+  const float* wgt;               // optional per-row weights: G = XS^T diag(w) XS (colsum, xty weighted too)
+  int col_lo;                     // column window [col_lo, col_lo + ncols) of the concatenated design
+  int ncols;
+  int n_tiles;                    // ceil(ncols / 64)
   int n_pairs;                    // n_tiles * (n_tiles + 1) / 2
   int n_slabs;
   double* part;                   // [n_slabs][ctot * ctot + 2 * ctot]
 };
 
 __device__ __forceinline__ float gram_load(const GramArgs& a, long long row, int col) {
-  if (col >= a.ctot || row >= a.n_rows) return 0.f;
+  if (col >= a.ncols || row >= a.n_rows) return 0.f;
+  col += a.col_lo;
   int s = 0;
   while (s + 1 < a.n_slots && col >= a.slot_col0[s + 1]) ++s;
   const float* p = a.slot_ptr[s];
@@ -62,8 +66,10 @@ __global__ void __launch_bounds__(256) gram_kernel(const GramArgs a) {
       const int k = e / kGramTile, c = e % kGramTile;
       const long long row = r0 + k;
       const bool ok = row < r_end;
-      Pa[k][c] = ok ? gram_load(a, row, ti * kGramTile + c) : 0.f;
-      Pb[k][c] = diag ? Pa[k][c] : (ok ? gram_load(a, row, tj * kGramTile + c) : 0.f);
+      const float wv = (a.wgt != nullptr && ok) ? __ldg(a.wgt + row) : 1.f;
+      const float xa = ok ? gram_load(a, row, ti * kGramTile + c) : 0.f;
+      Pa[k][c] = xa * wv;                                   // the weight rides on the left factor
+      Pb[k][c] = diag ? xa : (ok ? gram_load(a, row, tj * kGramTile + c) : 0.f);
     }
     if (threadIdx.x < kGramKC) {
       const long long row = r0 + threadIdx.x;
@@ -91,23 +97,32 @@ __global__ void __launch_bounds__(256) gram_kernel(const GramArgs a) {
     }
     __syncthreads();
   }
-  double* out = a.part + (size_t)slab * ((size_t)a.ctot * a.ctot + 2 * (size_t)a.ctot);
+  double* out = a.part + (size_t)slab * ((size_t)a.ncols * a.ncols + 2 * (size_t)a.ncols);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = ti * kGramTile + ty * 4 + i, c = tj * kGramTile + tx * 4 + j;
-      if (r < a.ctot && c < a.ctot) {
-        out[(size_t)r * a.ctot + c] = acc[i][j];
-        if (!diag) out[(size_t)c * a.ctot + r] = acc[i][j];
+      if (r < a.ncols && c < a.ncols) {
+        out[(size_t)r * a.ncols + c] = acc[i][j];
+        if (!diag) out[(size_t)c * a.ncols + r] = acc[i][j];
       }
     }
   if (diag && threadIdx.x < kGramTile) {
     const int c = ti * kGramTile + threadIdx.x;
-    if (c < a.ctot) {
-      out[(size_t)a.ctot * a.ctot + c] = cs;
-      out[(size_t)a.ctot * a.ctot + a.ctot + c] = cy;
+    if (c < a.ncols) {
+      out[(size_t)a.ncols * a.ncols + c] = cs;
+      out[(size_t)a.ncols * a.ncols + a.ncols + c] = cy;
     }
+  }
+}
+
+// w <- 1 / r^2 in place (the weights of the Poisson filter covariance, _glm.py:1129-1131)
+__global__ void __launch_bounds__(256) inv_square_kernel(float* r, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = r[i];
+    r[i] = 1.0f / (v * v);
   }
 }
 

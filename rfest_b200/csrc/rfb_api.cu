@@ -1266,8 +1266,10 @@ extern "C" int rfb_model_get_params(rfb_model* m, float* b, double* intercepts) 
   return RFB_OK;
 }
 
+// only_filter >= 0: evaluate that filter alone with all intercepts zero (the `u` of
+// _get_filter_variance, _glm.py:1125-1131); keep_r: leave the predictions in ds.r_buf on the device.
 static int eval_impl(rfb_model* m, int kind, const float* b, const double* intercepts, float* r_out,
-                     double* sums, double* grad_b, double* grad_ic) {
+                     double* sums, double* grad_b, double* grad_ic, int only_filter = -1, bool keep_r = false) {
   if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
   if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
   DataSet& ds = m->data[kind];
@@ -1293,7 +1295,7 @@ static int eval_impl(rfb_model* m, int kind, const float* b, const double* inter
   std::vector<char> head_live(p.Ht, 0);
   for (int f = 0; f < p.F; ++f) {
     const int s = m->filters[f].slot;
-    const bool present = s < ds.n_slots && ds.blocks[s] != nullptr;
+    const bool present = s < ds.n_slots && ds.blocks[s] != nullptr && (only_filter < 0 || only_filter == f);
     if (present) {
       head_live[p.head_of[f]] = 1;
     } else {
@@ -1303,6 +1305,8 @@ static int eval_impl(rfb_model* m, int kind, const float* b, const double* inter
   }
   for (int h = 0; h < p.H; ++h)
     if (!head_live[h]) head_nl[h] = kNlAbsent;
+  if (only_filter >= 0)
+    for (auto& c : hic) c = 0.0;
   CU(cudaMemcpyAsync(m->tmp.theta, hb.data(), sizeof(float) * p.P, cudaMemcpyHostToDevice, e->stream));
   CU(cudaMemcpyAsync(m->tmp.ic, hic.data(), sizeof(double) * (p.F + 1), cudaMemcpyHostToDevice, e->stream));
   publish_params_kernel<<<1, kUpdateThreads, 0, e->stream>>>(publish_args(m, m->tmp));
@@ -1310,7 +1314,7 @@ static int eval_impl(rfb_model* m, int kind, const float* b, const double* inter
   CU(cudaGetLastError());
 
   float* d_r = nullptr;
-  if (r_out) {
+  if (r_out || keep_r) {
     if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * ((size_t)ds.n + 4)));
     d_r = ds.r_buf;
   }
@@ -1364,17 +1368,13 @@ extern "C" int rfb_model_value_and_grad(rfb_model* m, int kind, const float* b, 
   return eval_impl(m, kind, b, intercepts, nullptr, sums, grad_b, grad_icpt);
 }
 
-extern "C" int rfb_model_gram(rfb_model* m, int kind, double* gram, double* colsum, double* xty, int* ctot_out) {
-  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
-  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+// Gram pieces over the column window [col_lo, col_lo + ncols) of the concatenated design, optionally
+// row-weighted; results (float64, all-reduced over ranks) are copied to the host.
+static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float* d_wgt, double* gram,
+                     double* colsum, double* xty) {
   DataSet& ds = m->data[kind];
-  if (!ds.bound) return fail(RFB_ERR_STATE, "no data bound for kind %d", kind);
-  TRY(ensure_plan(m));
   const Plan& p = m->plan;
-  if (ctot_out) *ctot_out = p.ctot;
-  if (!gram && !colsum && !xty) return RFB_OK;     // size query
   rfb_engine* e = m->e;
-  TRY(use_device(e));
   GramArgs a{};
   a.n_slots = p.n_slots;
   for (int s = 0; s < p.n_slots; ++s) {
@@ -1386,13 +1386,16 @@ extern "C" int rfb_model_gram(rfb_model* m, int kind, double* gram, double* cols
   a.ctot = p.ctot;
   a.n_rows = ds.n;
   a.y = ds.has_y ? ds.y : nullptr;
-  a.n_tiles = (p.ctot + kGramTile - 1) / kGramTile;
+  a.wgt = d_wgt;
+  a.col_lo = col_lo;
+  a.ncols = ncols;
+  a.n_tiles = (ncols + kGramTile - 1) / kGramTile;
   a.n_pairs = a.n_tiles * (a.n_tiles + 1) / 2;
   // enough slabs to fill the chip about twice, but never shorter than 4096 rows
   int slabs = std::max(1, (2 * e->num_sms + a.n_pairs - 1) / a.n_pairs);
   slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, ds.n / 4096));
   a.n_slabs = slabs;
-  const size_t n_entries = (size_t)p.ctot * p.ctot + 2 * (size_t)p.ctot;
+  const size_t n_entries = (size_t)ncols * ncols + 2 * (size_t)ncols;
   double *d_part = nullptr, *d_out = nullptr;
   CU(cudaMalloc(&d_part, sizeof(double) * n_entries * slabs));
   CU(cudaMalloc(&d_out, sizeof(double) * n_entries));
@@ -1406,15 +1409,50 @@ extern "C" int rfb_model_gram(rfb_model* m, int kind, double* gram, double* cols
   if (ce != cudaSuccess) rc = fail(RFB_ERR_CUDA, "gram kernel failed: %s", cudaGetErrorString(ce));
   if (rc == RFB_OK) rc = allreduce_device_f64(e, d_out, n_entries);
   if (rc == RFB_OK) {
-    const size_t cc = (size_t)p.ctot * p.ctot;
+    const size_t cc = (size_t)ncols * ncols;
     if (gram) cudaMemcpyAsync(gram, d_out, sizeof(double) * cc, cudaMemcpyDeviceToHost, e->stream);
-    if (colsum) cudaMemcpyAsync(colsum, d_out + cc, sizeof(double) * p.ctot, cudaMemcpyDeviceToHost, e->stream);
-    if (xty) cudaMemcpyAsync(xty, d_out + cc + p.ctot, sizeof(double) * p.ctot, cudaMemcpyDeviceToHost, e->stream);
+    if (colsum) cudaMemcpyAsync(colsum, d_out + cc, sizeof(double) * ncols, cudaMemcpyDeviceToHost, e->stream);
+    if (xty) cudaMemcpyAsync(xty, d_out + cc + ncols, sizeof(double) * ncols, cudaMemcpyDeviceToHost, e->stream);
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(RFB_ERR_CUDA, "gram copy-back failed");
   }
   cudaFree(d_part);
   cudaFree(d_out);
   return rc;
+}
+
+extern "C" int rfb_model_gram(rfb_model* m, int kind, double* gram, double* colsum, double* xty, int* ctot_out) {
+  if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  if (!m->data[kind].bound) return fail(RFB_ERR_STATE, "no data bound for kind %d", kind);
+  TRY(ensure_plan(m));
+  if (ctot_out) *ctot_out = m->plan.ctot;
+  if (!gram && !colsum && !xty) return RFB_OK;     // size query
+  TRY(use_device(m->e));
+  return gram_impl(m, kind, 0, m->plan.ctot, nullptr, gram, colsum, xty);
+}
+
+extern "C" int rfb_model_filter_gram(rfb_model* m, int kind, int filter, const float* b, int weighted, double* gram) {
+  if (!m || !gram) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  DataSet& ds = m->data[kind];
+  if (!ds.bound) return fail(RFB_ERR_STATE, "no data bound for kind %d", kind);
+  TRY(ensure_plan(m));
+  const Plan& p = m->plan;
+  if (filter < 0 || filter >= p.F) return fail(RFB_ERR_INVALID, "filter %d out of range", filter);
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  const Filter& fl = m->filters[filter];
+  const float* d_w = nullptr;
+  if (weighted) {
+    if (!b) return fail(RFB_ERR_INVALID, "the weighted Gram needs the coefficients");
+    std::vector<double> ic(p.F + 1, 0.0);
+    TRY(eval_impl(m, kind, b, ic.data(), nullptr, nullptr, nullptr, nullptr, filter, true));
+    inv_square_kernel<<<(unsigned)((ds.n + 255) / 256), 256, 0, e->stream>>>(ds.r_buf, ds.n);
+    e->launches++;
+    CU(cudaGetLastError());
+    d_w = ds.r_buf;
+  }
+  return gram_impl(m, kind, 4 * p.slot_chunk0[fl.slot], fl.n_coef, d_w, gram, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -329,6 +329,16 @@ class DeviceModel:
                                       s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.byref(c)))
         return G, s, t
 
+    def filter_gram(self, kind, filter_index, n_coef, b=None, weighted=False):
+        """XS_f^T diag(U) XS_f of one filter in float64 (see rfb_model_filter_gram)."""
+        G = np.empty((n_coef, n_coef), dtype=np.float64)
+        bb = np.ascontiguousarray(b, dtype=np.float32) if b is not None else None
+        check(self.lib.rfb_model_filter_gram(
+            self.handle, _lib.KIND[kind], int(filter_index),
+            bb.ctypes.data_as(C.c_void_p) if bb is not None else None, int(bool(weighted)),
+            G.ctypes.data_as(C.c_void_p)))
+        return G
+
     # ---- fit loop ------------------------------------------------------------------------
     def fit_begin(self, step_sizes, alpha, beta, metric):
         steps = np.ascontiguousarray(step_sizes, dtype=np.float64)

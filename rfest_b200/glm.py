@@ -350,11 +350,13 @@ class GLM:
 
     def initialize(self, y=None, num_subunits=1, dt=0.033, method="random", compute_ci=True,
                    random_seed=2046, verbose=0, add_noise_to_mle=False):
-        """_glm.py:395-436.  Confidence intervals (`compute_ci`) are not part of this engine."""
+        """_glm.py:395-436.  `compute_ci` gives the coefficient covariances `V`, `b_se`, `w_se`
+        (`_get_filter_variance`); the response confidence bands of the reference
+        (`_get_response_variance`) need the n x prod(dims) lagged matrix and are not available."""
         self.dt = dt
         self.init_method = method
         self.num_subunits = num_subunits
-        self.compute_ci = False
+        self.compute_ci = compute_ci
         if method == "random":
             self._initialize_random(verbose=verbose, random_seed=random_seed)
         elif method == "mle":
@@ -433,9 +435,48 @@ class GLM:
                          for name in self.filter_names}
         self.p["mle"]["intercept"] = self.intercept["mle"]
         self.y_pred["mle"] = {"train": self.forwardpass(self.p["mle"], kind="train")}
+        if self.compute_ci is None:
+            self.compute_ci = compute_ci
+        if self.compute_ci:
+            self._get_filter_variance(w_type="mle")
         if y_dev is not None:
             self.y_pred["mle"]["dev"] = self.forwardpass(self.p["mle"], kind="dev")
         self.mle_computed = True
+
+    def _get_filter_variance(self, w_type="opt"):
+        """_glm.py:1058-1164: covariance and standard errors of every filter's coefficients.
+
+        Gaussian: V = inv(XS^T XS) * rss / (n - sum(df)); otherwise V = inv(XS^T diag(U) XS) with
+        U = 1 / fnl(fnl(XS b, filter_nl), output_nl)^2.  The (weighted) Gram matrices are computed on
+        the device in float64 (csrc/gram.cuh), the small inverses on the host."""
+        self._sync()
+        p = self.p[w_type]
+        b_flat, ic = self._flatten(p)
+        n = float(self._n_trim["train"])
+        gaussian = self.distr == "gaussian"
+        if gaussian:
+            _, sums = self._dm.eval("train", b_flat, ic)
+            rss = sums[_lib.SUM_SQERR]                                            # _glm.py:1070-1071
+        V, b_se, w_se = {}, {}, {}
+        for i, name in enumerate(self.filter_names):
+            k = self.n_features[name]
+            if n < (sum(self.df[name]) if name in self.S else k):
+                print("Sample size is too small for getting reasonable confidence interval.")
+            G = self._dm.filter_gram("train", i, k, b=b_flat, weighted=not gaussian)
+            try:
+                Vn = np.linalg.inv(G)
+            except np.linalg.LinAlgError:
+                Vn = np.linalg.pinv(G)
+            if gaussian:
+                Vn = Vn * (rss / (n - sum(self.df[name] if name in self.df else self.dims[name])))
+            V[name] = np.abs(Vn)                                                 # _glm.py:1095,1138
+            se = np.sqrt(np.diag(V[name]))
+            if name in self.S:
+                b_se[name] = se
+                w_se[name] = self.S[name] @ se
+            else:
+                w_se[name] = se
+        self.V[w_type], self.b_se[w_type], self.w_se[w_type] = V, b_se, w_se
 
     # ------------------------------------------------------------------------------------
     # device model plumbing
@@ -764,6 +805,8 @@ class GLM:
             else:
                 self.w["opt"][name] = self.p["opt"][name]
         self.intercept["opt"] = self.p["opt"]["intercept"]
+        if self.compute_ci:                                                       # _glm.py:932-933
+            self._get_filter_variance(w_type="opt")
 
     # ------------------------------------------------------------------------------------
     # prediction / scoring

@@ -17,7 +17,7 @@ def build_and_fit(GLM, stim, y, n_tr, iters, device=None):
     m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
     m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
     m.add_design_matrix(y[n_tr:], name="history", kind="dev")
-    m.initialize(method="random", random_seed=3)
+    m.initialize(method="random", random_seed=3, compute_ci=False)
     for k, name in enumerate(m.filter_names):
         m.p0[name] = (0.1 * np.random.default_rng(70 + k).standard_normal(m.p0[name].shape)).astype(np.float32)
     m.fit(y={"train": y[:n_tr], "dev": y[n_tr:]}, num_iters=iters, step_size=0.05, beta=0.01,

@@ -438,3 +438,33 @@ def test_value_and_grad_matches_oracle(distr, out_nl, filt_nl, subunits):
         assert np.abs(gg[name] - go[name]).max() < 2e-5 * scale
         assert abs(gg["intercept"][name] - go["intercept"][name]) < 2e-5 * max(1.0, abs(go["intercept"][name]))
     assert abs(gg["intercept"]["global"] - go["intercept"]["global"]) < 2e-5 * max(1.0, abs(go["intercept"]["global"]))
+
+
+@pytest.mark.parametrize("distr,out_nl,filt_nl", [("poisson", "softplus", "none"), ("gaussian", "none", "none"),
+                                                 ("poisson", "exponential", "softplus")])
+def test_filter_covariance_matches_oracle(distr, out_nl, filt_nl):
+    """compute_ci: V, b_se, w_se of _get_filter_variance (_glm.py:1058-1164) -- the inputs of the
+    reference's Wald significance test (rfest/check.py:103-126)."""
+    stim, y, _ = helpers.lnp_data(3000, (8, 5, 4), seed=21)
+    if distr == "gaussian":
+        y = (y - y.mean()).astype(np.float32)
+    g, o = _pair(distr, out_nl)
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity=filt_nl,
+                            name="stimulus")
+        m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(method="random", random_seed=3)          # compute_ci defaults to True, as in the reference
+    _same_p0([o, g], scale=0.1)
+    for m in (g, o):
+        m.fit(y=y, num_iters=20, step_size=0.02, beta=0.01, verbose=0, tolerance=0)
+    assert g.compute_ci and set(g.V["opt"]) == set(o.V["opt"]) == {"stimulus", "history"}
+    for name in o.filter_names:
+        Vo, Vg = o.V["opt"][name], g.V["opt"][name]
+        assert Vg.shape == Vo.shape
+        assert np.abs(Vg - Vo).max() < 2e-3 * np.abs(Vo).max()
+        assert _wrel(g.b_se["opt"][name], o.b_se["opt"][name]) < 1e-3
+        assert _wrel(g.w_se["opt"][name], o.w_se["opt"][name]) < 1e-3
+        # Wald statistic of check.significance
+        Wg = float(np.squeeze(g.p["opt"][name].T @ np.linalg.inv(Vg) @ g.p["opt"][name]))
+        Wo = float(np.squeeze(o.p["opt"][name].T @ np.linalg.inv(Vo) @ o.p["opt"][name]))
+        assert abs(Wg - Wo) < 5e-3 * abs(Wo)

@@ -28,7 +28,7 @@ def _build(log2n, dims, df, distr, out_nl, history):
     m.add_design_matrix(stim, dims=dims, df=df, smooth="cr", name="stimulus")
     if history:
         m.add_design_matrix(TensorRows(y, 0, n_raw), dims=[20], df=[8], smooth="cr", shift=1, name="history")
-    m.initialize(method="random", random_seed=2046)
+    m.initialize(method="random", random_seed=2046, compute_ci=False)
     m.alpha, m.beta = 1.0, 0.0
     m.y["train"] = y[dims[0] - 1:].cpu().numpy()
     m._dirty = True

@@ -51,7 +51,7 @@ def run(cid):
         if c["history"]:
             kw = dict(dims=[20], df=[8], smooth="cr", shift=1) if kind == "train" else {}
             m.add_design_matrix(TensorRows(y[a:b], 0, b - a), name="history", kind=kind, **kw)
-    m.initialize(num_subunits=c["subunits"], method="random", random_seed=2046)
+    m.initialize(num_subunits=c["subunits"], method="random", random_seed=2046, compute_ci=False)
     for i, name in enumerate(m.filter_names):
         m.p0[name] = (0.1 * np.random.default_rng(2046 + i).standard_normal(m.p0[name].shape)).astype(np.float32)
     eng.synchronize()

@@ -24,7 +24,7 @@ y = poisson_response(eng, stim, DIMS, 0, n_raw)
 m = GLM(distr="poisson", output_nonlinearity="softplus", device=0)
 m.add_design_matrix(stim, dims=DIMS, df=DF, smooth="cr", name="stimulus")
 m.add_design_matrix(TensorRows(y, 0, n_raw), dims=[20], df=[8], smooth="cr", shift=1, name="history")
-m.initialize(method="random", random_seed=2046)
+m.initialize(method="random", random_seed=2046, compute_ci=False)
 for i, name in enumerate(m.filter_names):
     m.p0[name] = (0.1 * np.random.default_rng(2046 + i).standard_normal(m.p0[name].shape)).astype(np.float32)
 m.alpha, m.beta = 1.0, 0.01
