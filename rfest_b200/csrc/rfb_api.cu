@@ -189,6 +189,7 @@ struct Plan {
   int Ht = 0;  // template head count (>= H)
   int NCH = 0; // template chunks per lane
   int RB = 0;
+  bool generic = false;   // shape outside the register-resident kernels: generic fallback sweep
   int n_slots = 0;
   int slot_chunk0[kMaxSlots + 1] = {};
   int n_chunks = 0, ctot = 0, NE = 0;
@@ -323,14 +324,14 @@ static int build_plan(rfb_model* m) {
   p.H = (int)heads.size();
   if (p.H > kMaxHeads)
     return fail(RFB_ERR_UNSUPPORTED, "%d dot products per sample (max %d)", p.H, kMaxHeads);
-  p.Ht = template_heads(p.H);
   const int nch = (p.n_chunks + 31) / 32;
-  if (nch > 10)
-    return fail(RFB_ERR_UNSUPPORTED, "%d design columns per sample (max 1280)", p.ctot);
-  p.NCH = template_chunks(nch);
-  if (!sweep_instance(p.Ht, p.NCH, true, false, 0, &p.RB)) {
-    // fall back to a larger head template that exists for this width
-    return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel for %d heads x %d columns", p.H, p.ctot);
+  p.Ht = p.H <= 5 ? template_heads(p.H) : p.H;
+  p.NCH = nch <= 10 ? template_chunks(nch) : nch;
+  if (p.H > 5 || nch > 10 || !sweep_instance(p.Ht, p.NCH, true, false, 0, &p.RB)) {
+    // too wide / too many heads for the register-resident kernels: generic fallback
+    p.generic = true;
+    p.Ht = p.H;
+    p.RB = kGenRB;
   }
   p.head_nl.assign(p.Ht, RFB_NL_NONE);
   for (int h = 0; h < p.H; ++h) p.head_nl[h] = heads[h].nl;
@@ -453,6 +454,23 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
   int RB = 0;
   const int warps = std::min(std::max(e->sweep_warps, 1), kSweepThreads / 32);
   const int threads = warps * 32;
+  if (p.generic) {
+    int o = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sweep_generic_kernel<true>, threads, 0));
+    const int64_t ntiles = (ds.n + kGenRB - 1) / kGenRB;
+    int64_t grid = (int64_t)e->num_sms * std::max(o, 1);
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, (ntiles + warps - 1) / warps));
+    sb.warp_acc_bytes = sizeof(double) * (size_t)grid * warps * p.NE;
+    sb.cta_part_bytes = sizeof(double) * (size_t)grid * p.NE;
+    CU(cudaMalloc(&sb.warp_acc, sb.warp_acc_bytes));
+    CU(cudaMalloc(&sb.cta_part, sb.cta_part_bytes));
+    sb.grid = (int)grid;
+    sb.threads = threads;
+    sb.staged = 0;
+    sb.stages = 0;
+    sb.smem = 0;
+    return RFB_OK;
+  }
   int staged = e->sweep_staged ? 1 : 0;
   int stages = e->sweep_stages;
   if (stages <= 0) {
@@ -516,11 +534,14 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   const Plan& p = m->plan;
   DataSet& ds = m->data[kind];
   rfb_engine* e = m->e;
-  int RB = 0;
+  int RB = p.RB;
   TRY(ensure_sweep_buffers(m, kind));
   SweepBuffers& sb = m->sb[kind];
-  SweepFn fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, sweep_spec(m, head_nl), &RB);
-  if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
+  SweepFn fn = nullptr;
+  if (!p.generic) {
+    fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, sweep_spec(m, head_nl), &RB);
+    if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
+  }
 
   SweepArgs a{};
   a.n_slots = p.n_slots;
@@ -548,7 +569,12 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   a.r_out = r_out;
   a.flush_tiles = std::max(1, 256 / RB);
   a.n_stages = sb.stages;
-  fn<<<sb.grid, sb.threads, sb.smem, e->stream>>>(a);
+  if (p.generic) {
+    if (bwd) sweep_generic_kernel<true><<<sb.grid, sb.threads, 0, e->stream>>>(a, p.Ht);
+    else sweep_generic_kernel<false><<<sb.grid, sb.threads, 0, e->stream>>>(a, p.Ht);
+  } else {
+    fn<<<sb.grid, sb.threads, sb.smem, e->stream>>>(a);
+  }
   e->launches++;
   CU(cudaGetLastError());
   return RFB_OK;

@@ -703,6 +703,160 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
   cta_reduce<H, NCH, BWD>(a, ctot, NE);
 }
 
+// ================================================================================================
+// Variant C -- generic fallback: any number of columns, up to 8 heads.  Nothing is kept in
+// registers across rows: the head weights are read through L1, and the gradient goes straight
+// into the warp's fp64 accumulator row (L2 resident) once per 4-row tile.  About 3x the memory
+// traffic of the register-resident kernels; used only for shapes those cannot take (e.g. a 3-D
+// filter without a spline basis: 7500 columns).
+// ================================================================================================
+constexpr int kGenRB = 4;
+constexpr int kGenHeads = 8;
+
+template <bool BWD>
+__global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __grid_constant__ SweepArgs a, int H) {
+  const int lane = threadIdx.x & 31;
+  const int wpc = blockDim.x >> 5;
+  const long long gw = (long long)blockIdx.x * wpc + (threadIdx.x >> 5);
+  const long long GW = (long long)gridDim.x * wpc;
+  const int ctot = a.n_chunks * 4;
+  const int NE = H * ctot + kNumScalars;
+  double* my_acc = a.warp_acc + (size_t)gw * NE;
+  for (int e = lane; e < NE; e += 32) my_acc[e] = 0.0;
+  __syncwarp();
+  const bool poisson = a.distr == RFB_DISTR_POISSON;
+  const float gic = a.glob_icpt[0];
+  const float hic_lane = lane < H ? a.head_icpt[lane] : 0.f;
+  const int kind_lane = lane < H ? a.head_nl[lane] : RFB_NL_NONE;
+  double sc[S_GHEAD];          // row scalars, lane 0
+  double sc_head = 0.0;        // head-intercept gradient, lane = head
+#pragma unroll
+  for (int k = 0; k < S_GHEAD; ++k) sc[k] = 0.0;
+
+  auto chunk_ptr = [&](int c, long long row) -> const float* {
+    int s = 0;
+    while (s + 1 < a.n_slots && c >= a.slot_chunk0[s + 1]) ++s;
+    const float* p = a.slot_ptr[s];
+    return p ? p + row * a.slot_ld[s] + 4 * (c - a.slot_chunk0[s]) : nullptr;
+  };
+
+  const long long ntiles = (a.n_rows + kGenRB - 1) / kGenRB;
+  for (long long tile = gw; tile < ntiles; tile += GW) {
+    const long long row0 = tile * kGenRB;
+    // pass 1: dot products of the tile's rows with every head
+    float acc[kGenHeads][kGenRB];
+#pragma unroll
+    for (int h = 0; h < kGenHeads; ++h)
+#pragma unroll
+      for (int r = 0; r < kGenRB; ++r) acc[h][r] = 0.f;
+    for (int c = lane; c < a.n_chunks; c += 32) {
+      float4 x[kGenRB];
+#pragma unroll
+      for (int r = 0; r < kGenRB; ++r) {
+        const float* p = (row0 + r < a.n_rows) ? chunk_ptr(c, row0 + r) : nullptr;
+        x[r] = p ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int h = 0; h < kGenHeads; ++h) {
+        if (h < H) {
+          const float4 w = *reinterpret_cast<const float4*>(a.W + (size_t)h * ctot + 4 * c);
+#pragma unroll
+          for (int r = 0; r < kGenRB; ++r)
+            acc[h][r] = fmaf(x[r].x, w.x, fmaf(x[r].y, w.y, fmaf(x[r].z, w.z, fmaf(x[r].w, w.w, acc[h][r]))));
+        }
+      }
+    }
+    // per row: warp sums, nonlinearities (lane = head), loss, delta
+    float delta_h[kGenRB];      // lane h: dL/da_{h, r}
+#pragma unroll
+    for (int r = 0; r < kGenRB; ++r) {
+      float mine = 0.f;         // lane h keeps the full dot product of head h
+#pragma unroll
+      for (int h = 0; h < kGenHeads; ++h) {
+        if (h < H) {
+          float v = acc[h][r];
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+          if (lane == h) mine = v;
+        }
+      }
+      float f, dphi;
+      nl_eval(kind_lane, mine + hic_lane, f, dphi);
+      float u = lane < H ? f : 0.f;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) u += __shfl_xor_sync(0xffffffffu, u, m);
+      u += gic;
+      float rr, dr;
+      nl_eval(a.out_nl, u, rr, dr);
+      const long long row = row0 + r;
+      const bool rowok = row < a.n_rows;
+      const float yv = (rowok && a.y != nullptr) ? __ldg(a.y + row) : 0.f;
+      float la, lb, dldr;
+      const float err = yv - rr;
+      if (poisson) {
+        const bool fin = rr != CUDART_INF_F;
+        const float r1 = fin ? rr : 0.f;
+        const bool live = fin && (r1 > 1e-20f);
+        const float r2 = (r1 != r1) ? r1 : fmaxf(r1, 1e-20f);
+        la = -logf(r2) * yv;
+        lb = r2;
+        dldr = live ? (1.0f - fast_div(yv, r2)) : 0.f;
+      } else {
+        la = err * err;
+        lb = 0.f;
+        dldr = -err * a.two_over_n;
+      }
+      const float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
+      if (rowok && lane == 0) {
+        sc[S_LOSS_A] += la; sc[S_LOSS_B] += lb; sc[S_R] += rr; sc[S_RR] += rr * rr;
+        sc[S_YR] += yv * rr; sc[S_SQERR] += err * err; sc[S_GGLOBAL] += delta;
+        if (a.r_out != nullptr) a.r_out[row] = rr;
+      }
+      delta_h[r] = (delta == 0.f || lane >= H) ? 0.f : delta * dphi;
+      sc_head += (double)delta_h[r];
+    }
+    // pass 2: gradient of the tile, added once per chunk into the fp64 accumulator row
+    if (BWD) {
+      for (int c = lane; c < a.n_chunks; c += 32) {
+        float4 x[kGenRB];
+#pragma unroll
+        for (int r = 0; r < kGenRB; ++r) {
+          const float* p = (row0 + r < a.n_rows) ? chunk_ptr(c, row0 + r) : nullptr;   // L1 / L2 hit
+          x[r] = p ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int h = 0; h < H; ++h) {
+          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < kGenRB; ++r) {
+            const float d = __shfl_sync(0xffffffffu, delta_h[r], h);
+            gsum.x = fmaf(d, x[r].x, gsum.x); gsum.y = fmaf(d, x[r].y, gsum.y);
+            gsum.z = fmaf(d, x[r].z, gsum.z); gsum.w = fmaf(d, x[r].w, gsum.w);
+          }
+          double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)h * ctot + 4 * c);
+          double2 lo = p2[0], hi = p2[1];
+          lo.x += (double)gsum.x; lo.y += (double)gsum.y; hi.x += (double)gsum.z; hi.y += (double)gsum.w;
+          p2[0] = lo;
+          p2[1] = hi;
+        }
+      }
+    } else {
+      // keep the shuffles of pass 2 out of the forward-only variant
+    }
+  }
+  if (lane == 0)
+    for (int k = 0; k < S_GHEAD; ++k) my_acc[(size_t)H * ctot + k] = sc[k];
+  if (lane < H) my_acc[(size_t)H * ctot + S_GHEAD + lane] = sc_head;
+
+  __syncthreads();
+  const double* cta_rows = a.warp_acc + (size_t)blockIdx.x * wpc * NE;
+  double* out = a.cta_part + (size_t)blockIdx.x * NE;
+  for (int e = (BWD ? 0 : H * ctot) + threadIdx.x; e < NE; e += blockDim.x) {
+    double s = 0.0;
+    for (int wv = 0; wv < wpc; ++wv) s += cta_rows[(size_t)wv * NE + e];
+    out[e] = s;
+  }
+}
+
 // out[e] = sum_p part[p][e]: thread x = entry, thread y = strided slice of the partials.
 constexpr int kReduceEx = 32, kReduceEy = 8;
 struct ReduceSeg {

@@ -468,3 +468,43 @@ def test_filter_covariance_matches_oracle(distr, out_nl, filt_nl):
         Wg = float(np.squeeze(g.p["opt"][name].T @ np.linalg.inv(Vg) @ g.p["opt"][name]))
         Wo = float(np.squeeze(o.p["opt"][name].T @ np.linalg.inv(Vo) @ o.p["opt"][name]))
         assert abs(Wg - Wo) < 5e-3 * abs(Wo)
+
+
+def test_generic_sweep_wide_design_without_basis():
+    """A 3-D filter with no spline basis: the design is the raw lagged stimulus (1800 columns, beyond the
+    register-resident kernels) -> generic fallback sweep."""
+    rng = np.random.default_rng(3)
+    n = 1303
+    stim = rng.standard_normal((n, 20, 15)).astype(np.float32)
+    y = rng.poisson(0.4, n).astype(np.float32)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[6, 20, 15], smooth=None, name="stimulus")
+        m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(method="random", random_seed=1, compute_ci=False)
+    assert g.n_features["stimulus"] == 1800
+    _same_p0([o, g], scale=0.01)
+    for m in (g, o):
+        m.fit(y=y, num_iters=25, step_size=0.002, beta=0.01, verbose=0, tolerance=0)
+    _compare_fit(g, o, False)
+    w = np.asarray(g.w["opt"]["stimulus"])
+    assert w.shape == (1800, 1)
+
+
+def test_generic_sweep_many_subunits():
+    """7 subunits + history = 8 dot products per sample (more than the specialised kernels take)."""
+    stim, y, _ = helpers.lnp_data(1800, (8, 5, 4), seed=17)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim[:1400], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity="softplus",
+                            name="stimulus")
+        m.add_design_matrix(stim[1400:], name="stimulus", kind="dev")
+        m.add_design_matrix(y[:1400], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.add_design_matrix(y[1400:], name="history", kind="dev")
+        m.initialize(num_subunits=7, method="random", random_seed=3, compute_ci=False)
+    _same_p0([o, g], scale=0.2, icpt=0.01)
+    for m in (g, o):
+        m.fit(y={"train": y[:1400], "dev": y[1400:]}, num_iters=30, alpha=0.5, beta=0.01, step_size=0.02,
+              verbose=0, tolerance=0)
+    assert len(g.filter_names) == 8
+    _compare_fit(g, o, True)
