@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
         }
       }
     }
+    __syncwarp();   // the chunk loop is lane-divergent; reconverge before the shuffles
     // per row: warp sums, nonlinearities (lane = head), loss, delta
     float delta_h[kGenRB];      // lane h: dL/da_{h, r}
 #pragma unroll
@@ -815,8 +816,14 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
       delta_h[r] = (delta == 0.f || lane >= H) ? 0.f : delta * dphi;
       sc_head += (double)delta_h[r];
     }
-    // pass 2: gradient of the tile, added once per chunk into the fp64 accumulator row
+    // pass 2: gradient of the tile, added once per chunk into the fp64 accumulator row.  The delta
+    // broadcasts happen before the (lane-divergent) chunk loop: no shuffles inside it.
     if (BWD) {
+      float d[kGenHeads][kGenRB];
+#pragma unroll
+      for (int h = 0; h < kGenHeads; ++h)
+#pragma unroll
+        for (int r = 0; r < kGenRB; ++r) d[h][r] = __shfl_sync(0xffffffffu, delta_h[r], h);
       for (int c = lane; c < a.n_chunks; c += 32) {
         float4 x[kGenRB];
 #pragma unroll
@@ -824,23 +831,24 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
           const float* p = (row0 + r < a.n_rows) ? chunk_ptr(c, row0 + r) : nullptr;   // L1 / L2 hit
           x[r] = p ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int h = 0; h < H; ++h) {
-          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int r = 0; r < kGenRB; ++r) {
-            const float d = __shfl_sync(0xffffffffu, delta_h[r], h);
-            gsum.x = fmaf(d, x[r].x, gsum.x); gsum.y = fmaf(d, x[r].y, gsum.y);
-            gsum.z = fmaf(d, x[r].z, gsum.z); gsum.w = fmaf(d, x[r].w, gsum.w);
+        for (int h = 0; h < kGenHeads; ++h) {
+          if (h < H) {
+            float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < kGenRB; ++r) {
+              gsum.x = fmaf(d[h][r], x[r].x, gsum.x); gsum.y = fmaf(d[h][r], x[r].y, gsum.y);
+              gsum.z = fmaf(d[h][r], x[r].z, gsum.z); gsum.w = fmaf(d[h][r], x[r].w, gsum.w);
+            }
+            double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)h * ctot + 4 * c);
+            double2 lo = p2[0], hi = p2[1];
+            lo.x += (double)gsum.x; lo.y += (double)gsum.y; hi.x += (double)gsum.z; hi.y += (double)gsum.w;
+            p2[0] = lo;
+            p2[1] = hi;
           }
-          double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)h * ctot + 4 * c);
-          double2 lo = p2[0], hi = p2[1];
-          lo.x += (double)gsum.x; lo.y += (double)gsum.y; hi.x += (double)gsum.z; hi.y += (double)gsum.w;
-          p2[0] = lo;
-          p2[1] = hi;
         }
       }
-    } else {
-      // keep the shuffles of pass 2 out of the forward-only variant
+      __syncwarp();
     }
   }
   if (lane == 0)
