@@ -134,6 +134,66 @@ __global__ void __launch_bounds__(128) temporal_project_kernel(const TemporalArg
   }
 }
 
+// Faster variant for nlag <= 64: the temporal basis sits in constant memory (padded with zero rows
+// to a multiple of 8 lags, so FFMAs take it as an operand through the constant cache), and the lag
+// loop is unrolled by 8 over a 15-value register window of Z, of which only 8 values are new per
+// step: one global load per 64 FMAs instead of 16.
+constexpr int kTempMaxLag = 64;
+__constant__ float c_st[kTempMaxLag * 16];
+
+template <int DFT>
+__global__ void __launch_bounds__(128) temporal_project_const_kernel(const TemporalArgs a) {
+  constexpr int TT = 8;
+  const long long n_groups = (a.n_out + TT - 1) / TT;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_groups * a.n_q) return;
+  const long long grp = item / a.n_q;
+  const int q = (int)(item - grp * a.n_q);
+  const long long k0 = grp * TT;
+  const long long src0 = a.first_t + k0 - a.front;     // raw row feeding (row k0, lag 0)
+
+  auto zload = [&](long long src) -> float {
+    if (src < 0 || src >= a.n_raw_total) return 0.f;
+    const long long zr = src - a.z_src0;
+    return (zr >= 0 && zr < a.n_z) ? __ldg(a.Z + zr * a.ldz + q) : 0.f;
+  };
+
+  float acc[TT][DFT];
+#pragma unroll
+  for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+    for (int d = 0; d < DFT; ++d) acc[tt][d] = 0.f;
+  float w[2 * TT - 1];                                  // Z[src0 + i0 + k], k = 0 .. 14
+#pragma unroll
+  for (int k = 0; k < TT - 1; ++k) w[k] = zload(src0 + k);
+  const int n_steps = (a.nlag + TT - 1) / TT;
+  for (int step = 0; step < n_steps; ++step) {
+    const int i0 = step * TT;
+#pragma unroll
+    for (int k = TT - 1; k < 2 * TT - 1; ++k) w[k] = zload(src0 + i0 + k);
+#pragma unroll
+    for (int j = 0; j < TT; ++j) {                      // lag i0 + j (zero basis rows past nlag)
+#pragma unroll
+      for (int d = 0; d < DFT; ++d) {
+        const float st = c_st[(i0 + j) * DFT + d];
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) acc[tt][d] = fmaf(w[tt + j], st, acc[tt][d]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TT - 1; ++k) w[k] = w[k + TT];
+  }
+#pragma unroll
+  for (int tt = 0; tt < TT; ++tt) {
+    const long long k = k0 + tt;
+    if (k >= a.n_out) break;
+    float* dst = a.out + (a.out_row0 + k) * a.out_ld + a.col0 + q;
+#pragma unroll
+    for (int d = 0; d < DFT; ++d)
+      if (d < a.df_t) dst[(size_t)d * a.n_q] = acc[tt][d];
+  }
+}
+
 // sum y, sum y^2 in fp64 (constants of the metrics, rfest/metrics.py:8-12)
 __global__ void __launch_bounds__(256) y_moments_kernel(const float* y, long long n, double* out2) {
   __shared__ double s0[8], s1[8];

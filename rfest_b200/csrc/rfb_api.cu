@@ -989,11 +989,16 @@ static bool tc_launch(rfb_engine* e, const TcPlan& tp, const float* d_stim, int6
 }
 
 template <int DFT>
-static void launch_temporal(const TemporalArgs& a, cudaStream_t s) {
+static void launch_temporal(const TemporalArgs& a, cudaStream_t s, bool use_const) {
+  const int threads = 128;
+  if (use_const) {   // temporal basis in constant memory, register window over the lags
+    const long long items = ((a.n_out + 7) / 8) * a.n_q;
+    temporal_project_const_kernel<DFT><<<(unsigned)((items + threads - 1) / threads), threads, 0, s>>>(a);
+    return;
+  }
   constexpr int TT = DFT <= 8 ? 8 : 4;
   const long long groups = (a.n_out + TT - 1) / TT;
   const long long items = groups * a.n_q;
-  const int threads = 128;
   const long long blocks = (items + threads - 1) / threads;
   temporal_project_kernel<DFT, TT><<<(unsigned)blocks, threads, 0, s>>>(a);
 }
@@ -1033,8 +1038,14 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
       for (int d = 0; d < df_t; ++d) stp[(size_t)i * DFT + d] = St[(size_t)i * df_t + d];
     TRY(scratch_reserve(e, e->stbuf, sizeof(float) * stp.size()));
     CU(cudaMemcpyAsync(e->stbuf.p, stp.data(), sizeof(float) * stp.size(), cudaMemcpyHostToDevice, e->stream));
+    if (nlag <= kTempMaxLag) {   // zero-padded copy in constant memory for the fast temporal kernel
+      std::vector<float> cst((size_t)kTempMaxLag * 16, 0.f);
+      std::copy(stp.begin(), stp.end(), cst.begin());
+      CU(cudaMemcpyToSymbolAsync(c_st, cst.data(), sizeof(float) * cst.size(), 0, cudaMemcpyHostToDevice, e->stream));
+    }
     CU(cudaStreamSynchronize(e->stream));
   }
+  const bool temporal_const = nlag <= kTempMaxLag && e->project_tc != 2;
   TcPlan tcp;
   TRY(tc_prepare(e, Sxy, n_pix, n_q, &tcp));
   const float* d_sxy = nullptr;
@@ -1098,12 +1109,12 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
     a.n_q = n_q;
     a.St = (const float*)e->stbuf.p;
     switch (DFT) {
-      case 1: launch_temporal<1>(a, e->stream); break;
-      case 2: launch_temporal<2>(a, e->stream); break;
-      case 4: launch_temporal<4>(a, e->stream); break;
-      case 8: launch_temporal<8>(a, e->stream); break;
-      case 12: launch_temporal<12>(a, e->stream); break;
-      default: launch_temporal<16>(a, e->stream); break;
+      case 1: launch_temporal<1>(a, e->stream, temporal_const); break;
+      case 2: launch_temporal<2>(a, e->stream, temporal_const); break;
+      case 4: launch_temporal<4>(a, e->stream, temporal_const); break;
+      case 8: launch_temporal<8>(a, e->stream, temporal_const); break;
+      case 12: launch_temporal<12>(a, e->stream, temporal_const); break;
+      default: launch_temporal<16>(a, e->stream, temporal_const); break;
     }
     e->launches++;
     CU(cudaGetLastError());
