@@ -15,19 +15,22 @@
 //   warp 8      A producer: per 32-wide K tile one 2-D TMA load (cp.async.bulk.tensor.2d,
 //               SWIZZLE_128B) of the raw 128 x 32 fp32 A tile into a deep ring of raw slots -- this ring
 //               is what keeps enough HBM bytes in flight.
-//   warp 10     B producer: TMA loads of the pre-split B_hi / B_lo tiles (N x 32, L2 resident) straight
-//               into the MMA ring.
-//   warps 4-7   splitters: read a landed raw slot, write A_hi = tf32(A) and A_lo = A - A_hi into the
-//               MMA ring with conflict-free 16-byte LDS/STS (the split is element-wise, hence
-//               layout-agnostic), fence the generic->async proxy, release the raw slot.
-//   warp 9      MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (4 k-steps x 3 products)
-//               per K tile from shared-memory descriptors into one of two TMEM accumulator sets;
-//               tcgen05.commit releases the MMA slot; every `drain` K tiles it publishes the set and
-//               switches to the other one.
+//   warp 10     B producer: TMA loads of the pre-split B_hi / B_lo tiles (N x 32, L2 resident) into
+//               a ring of shared-memory stages.
+//   warps 4-7   splitters: thread = row.  Read the row's 32 values of a landed raw slot (8 LDS.128
+//               following the 128-byte swizzle, conflict-free), form A_hi = tf32(A) and
+//               A_lo = A - A_hi in registers and write them straight into TENSOR MEMORY with
+//               tcgen05.st -- the A operands never go back to shared memory.
+//   warp 9      MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 per K tile (4 k-steps x
+//               3 products), A from TMEM, B from shared-memory descriptors, D in TMEM;
+//               tcgen05.commit releases the A / B stages; every `drain` K tiles it publishes the
+//               accumulator and switches to the other one.
 //   warps 0-3   accumulate + epilogue: tcgen05.ld the published partial sums (lane = row), add them
 //               into fp32 registers with round-to-nearest, and store the finished 128 x N tile of Z.
-// Keeping the TMEM accumulation chains short (4 * drain MMAs) is what holds fp32-level accuracy: the
+// Keeping the TMEM accumulation chains short (12 * drain MMAs) is what holds fp32-level accuracy: the
 // tensor core adds into its accumulator with truncation (measured bias ~ -0.5 ulp per MMA).
+// Shared-memory traffic per K tile: 16 KB TMA write + 16 KB split read + 2 N x 128 B TMA write + 3 N x 128 B
+// MMA reads (102 KB at N = 112) -- with SS-mode A operands it was 182 KB and bound the kernel.
 #pragma once
 
 #include <cuda.h>
@@ -46,18 +49,19 @@ struct TcArgs {
   int n_k_tiles;      // ceil(K / 32)
   int n;              // real N (columns of Z)
   int n_pad;          // UMMA N (multiple of 16, <= 128)
-  int n_stages;       // MMA ring slots (A_hi, A_lo, B_hi, B_lo)
+  int n_stages;       // B ring slots (B_hi, B_lo)
   float* Z;           // [M x ldz]
   int ldz;
-  int tmem_cols;      // power of two >= 4 * n_pad (two sets of {hi.hi, cross terms})
+  int tmem_cols;      // power of two >= 2 * n_pad (two accumulators) + 128 (two A stages of hi|lo)
   int drain;          // K tiles accumulated in TMEM before the partial sums move to registers
   int n_raw;          // raw A slots
 };
 
 constexpr size_t kTcRawBytes = (size_t)kTcM * kTcK * sizeof(float);   // 16 KB
 __host__ __device__ inline size_t tc_stage_bytes(int n_pad) {
-  return 2 * kTcRawBytes + (size_t)2 * n_pad * kTcK * sizeof(float);
+  return (size_t)2 * n_pad * kTcK * sizeof(float);
 }
+constexpr int kTcAStages = 2;        // A stages in tensor memory: 32 columns hi + 32 columns lo each
 __host__ __device__ inline size_t tc_smem_bytes(int n_pad, int stages, int n_raw) {
   return 1024 /* alignment slack */ + (size_t)stages * tc_stage_bytes(n_pad) + (size_t)n_raw * kTcRawBytes +
          512 /* barriers */;
@@ -108,6 +112,27 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -131,23 +156,22 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
   const uint32_t base = (tc::s32(tc_smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = (uint32_t)kTcRawBytes;
   const uint32_t b_bytes = (uint32_t)a.n_pad * kTcK * sizeof(float);
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const int NS = a.n_stages, NR = a.n_raw;
-  auto st_ahi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
-  auto st_alo = [&](int s) { return base + (uint32_t)s * stage_bytes + a_bytes; };
-  auto st_bhi = [&](int s) { return base + (uint32_t)s * stage_bytes + 2 * a_bytes; };
-  auto st_blo = [&](int s) { return base + (uint32_t)s * stage_bytes + 2 * a_bytes + b_bytes; };
+  const uint32_t stage_bytes = 2 * b_bytes;
+  const int NS = a.n_stages, NR = a.n_raw, NA = kTcAStages;
+  auto st_bhi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
+  auto st_blo = [&](int s) { return base + (uint32_t)s * stage_bytes + b_bytes; };
   const uint32_t raw0 = base + (uint32_t)NS * stage_bytes;
   auto st_raw = [&](int r) { return raw0 + (uint32_t)r * a_bytes; };
   const uint32_t bars = raw0 + (uint32_t)NR * a_bytes;              // 8-byte mbarriers
-  auto bar_rfull = [&](int r) { return bars + 8u * r; };               // raw A landed            (tx)
-  auto bar_rempty = [&](int r) { return bars + 8u * (NR + r); };       // raw slot consumed       (128)
-  auto bar_split = [&](int s) { return bars + 8u * (2 * NR + s); };    // A_hi / A_lo written     (128)
-  auto bar_bfull = [&](int s) { return bars + 8u * (2 * NR + NS + s); };      // B tiles landed   (tx)
-  auto bar_mempty = [&](int s) { return bars + 8u * (2 * NR + 2 * NS + s); }; // MMAs read slot   (1)
-  auto bar_tfull = [&](int b) { return bars + 8u * (2 * NR + 3 * NS + b); };      // partial sums published (1)
-  auto bar_tempty = [&](int b) { return bars + 8u * (2 * NR + 3 * NS + 2 + b); }; // ... drained       (128)
-  const uint32_t tmem_slot = bars + 8u * (2 * NR + 3 * NS + 4);
+  auto bar_rfull = [&](int r) { return bars + 8u * r; };               // raw A landed              (tx)
+  auto bar_rempty = [&](int r) { return bars + 8u * (NR + r); };       // raw slot read             (128)
+  auto bar_bfull = [&](int s) { return bars + 8u * (2 * NR + s); };    // B tiles landed            (tx)
+  auto bar_bempty = [&](int s) { return bars + 8u * (2 * NR + NS + s); };      // MMAs read B stage (1)
+  auto bar_afull = [&](int s) { return bars + 8u * (2 * NR + 2 * NS + s); };   // A hi|lo in TMEM   (128)
+  auto bar_aempty = [&](int s) { return bars + 8u * (2 * NR + 2 * NS + NA + s); };  // MMAs read A stage (1)
+  auto bar_tfull = [&](int b) { return bars + 8u * (2 * NR + 2 * NS + 2 * NA + b); };      // partial sums published (1)
+  auto bar_tempty = [&](int b) { return bars + 8u * (2 * NR + 2 * NS + 2 * NA + 2 + b); }; // ... drained       (128)
+  const uint32_t tmem_slot = bars + 8u * (2 * NR + 2 * NS + 2 * NA + 4);
 
   if (threadIdx.x == 0) {
     for (int r = 0; r < NR; ++r) {
@@ -155,9 +179,12 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       tc::mbar_init(bar_rempty(r), 128);
     }
     for (int s = 0; s < NS; ++s) {
-      tc::mbar_init(bar_split(s), 128);
       tc::mbar_init(bar_bfull(s), 1);
-      tc::mbar_init(bar_mempty(s), 1);
+      tc::mbar_init(bar_bempty(s), 1);
+    }
+    for (int s = 0; s < NA; ++s) {
+      tc::mbar_init(bar_afull(s), 128);
+      tc::mbar_init(bar_aempty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(bar_tfull(b), 1);
@@ -175,6 +202,9 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // tensor-memory map: [accumulator 0 | accumulator 1 | A stage 0: hi(32) lo(32) | A stage 1 ...]
+  const uint32_t tm_acc = tmem_base;
+  const uint32_t tm_a = tmem_base + (uint32_t)(2 * a.n_pad);
 
   const long long n_tiles = (a.n_rows + kTcM - 1) / kTcM;
   const int KT = a.n_k_tiles;
@@ -194,13 +224,13 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       }
     }
   } else if (warp == 10) {
-    // ================= B producer (MMA ring) =================
+    // ================= B producer =================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int kt = 0; kt < KT; ++kt) {
-          tc::mbar_wait(bar_mempty(s), ph ^ 1u);
+          tc::mbar_wait(bar_bempty(s), ph ^ 1u);
           tc::mbar_expect_tx(bar_bfull(s), 2 * b_bytes);
           tc::tma_load_2d(st_bhi(s), &map_bhi, kt * kTcK, 0, bar_bfull(s));
           tc::tma_load_2d(st_blo(s), &map_blo, kt * kTcK, 0, bar_bfull(s));
@@ -213,32 +243,33 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B tf32, both K-major, N = n_pad, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-      int s = 0, buf = 0;
-      uint32_t ph = 0, tph = 0;
+      int sb = 0, sa = 0, buf = 0;
+      uint32_t phb = 0, pha = 0, tph = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int kt = 0; kt < KT; ++kt) {
-          const bool first = (kt % a.drain) == 0;          // first K tile into this accumulator set
+          const bool first = (kt % a.drain) == 0;          // first K tile into this accumulator
           if (first) {
             tc::mbar_wait(bar_tempty(buf), tph ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          const uint32_t d_main = tmem_base + (uint32_t)(buf * 2 * a.n_pad);
-          const uint32_t d_small = d_main + (uint32_t)a.n_pad;
-          tc::mbar_wait(bar_split(s), ph);
-          tc::mbar_wait(bar_bfull(s), ph);
+          const uint32_t d = tm_acc + (uint32_t)(buf * a.n_pad);
+          tc::mbar_wait(bar_afull(sa), pha);
+          tc::mbar_wait(bar_bfull(sb), phb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = tm_a + (uint32_t)(sa * 64), a_lo = a_hi + 32u;
 #pragma unroll
           for (int ks = 0; ks < kTcK / 8; ++ks) {
-            const uint32_t off = (uint32_t)ks * 32u;   // 8 tf32 = 32 bytes along K inside the swizzle atom
-            const uint64_t ahi = tc::smem_desc(st_ahi(s) + off), alo = tc::smem_desc(st_alo(s) + off);
-            const uint64_t bhi = tc::smem_desc(st_bhi(s) + off), blo = tc::smem_desc(st_blo(s) + off);
-            const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-            tc::mma_tf32(d_small, alo, bhi, idesc, acc);
-            tc::mma_tf32(d_small, ahi, blo, idesc, 1);
-            tc::mma_tf32(d_main, ahi, bhi, idesc, acc);
+            const uint32_t off = (uint32_t)ks * 32u;       // 8 tf32 = 32 bytes along K inside the swizzle atom
+            const uint64_t bhi = tc::smem_desc(st_bhi(sb) + off), blo = tc::smem_desc(st_blo(sb) + off);
+            const uint32_t kc = (uint32_t)ks * 8u;          // 8 tensor-memory columns per k-step
+            tc::mma_tf32_ts(d, a_lo + kc, bhi, idesc, (first && ks == 0) ? 0u : 1u);
+            tc::mma_tf32_ts(d, a_hi + kc, blo, idesc, 1);
+            tc::mma_tf32_ts(d, a_hi + kc, bhi, idesc, 1);
           }
-          tc::commit(bar_mempty(s));         // slot reusable once these MMAs have read it
-          if (++s == NS) { s = 0; ph ^= 1u; }
+          tc::commit(bar_aempty(sa));        // stages reusable once these MMAs have read them
+          tc::commit(bar_bempty(sb));
+          if (++sa == NA) { sa = 0; pha ^= 1u; }
+          if (++sb == NS) { sb = 0; phb ^= 1u; }
           if ((kt % a.drain) == a.drain - 1 || kt == KT - 1) {
             tc::commit(bar_tfull(buf));      // partial sums complete
             if (++buf == 2) { buf = 0; tph ^= 1u; }
@@ -247,31 +278,40 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       }
     }
   } else if (warp >= 4) {
-    // ================= splitters (warps 4-7, 128 threads) =================
+    // ================= splitters (warps 4-7: thread = row of the tile = TMEM lane) =================
     const int t = threadIdx.x - 128;
-    int s = 0, r = 0;
-    uint32_t ph = 0, rph = 0;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int r = 0, sa = 0;
+    uint32_t rph = 0, pha = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kt = 0; kt < KT; ++kt) {
         tc::mbar_wait(bar_rfull(r), rph);
-        tc::mbar_wait(bar_mempty(s), ph ^ 1u);
-        const uint32_t src = st_raw(r), hi_base = st_ahi(s), lo_base = st_alo(s);
+        const uint32_t row_addr = st_raw(r) + (uint32_t)t * 128u;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < (kTcM * kTcK / 4) / 128; ++i) {      // 1024 16-byte chunks / 128 threads
-          const uint32_t off = (uint32_t)(t + 128 * i) * 16u;
+        for (int j = 0; j < 8; ++j) {                       // chunk j of row t sits at j ^ (t & 7)
           uint32_t x0, x1, x2, x3;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(src + off));
-          const uint32_t h0 = x0 & 0xFFFFE000u, h1 = x1 & 0xFFFFE000u, h2 = x2 & 0xFFFFE000u, h3 = x3 & 0xFFFFE000u;
-          const float l0 = __uint_as_float(x0) - __uint_as_float(h0), l1 = __uint_as_float(x1) - __uint_as_float(h1);
-          const float l2 = __uint_as_float(x2) - __uint_as_float(h2), l3 = __uint_as_float(x3) - __uint_as_float(h3);
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(l0), "f"(l1), "f"(l2), "f"(l3) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                       : "r"(row_addr + (uint32_t)((j ^ (t & 7)) << 4)));
+          hi[4 * j + 0] = x0 & 0xFFFFE000u; hi[4 * j + 1] = x1 & 0xFFFFE000u;
+          hi[4 * j + 2] = x2 & 0xFFFFE000u; hi[4 * j + 3] = x3 & 0xFFFFE000u;
+          lo[4 * j + 0] = __float_as_uint(__uint_as_float(x0) - __uint_as_float(hi[4 * j + 0]));
+          lo[4 * j + 1] = __float_as_uint(__uint_as_float(x1) - __uint_as_float(hi[4 * j + 1]));
+          lo[4 * j + 2] = __float_as_uint(__uint_as_float(x2) - __uint_as_float(hi[4 * j + 2]));
+          lo[4 * j + 3] = __float_as_uint(__uint_as_float(x3) - __uint_as_float(hi[4 * j + 3]));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
-        tc::mbar_arrive(bar_split(s));
-        tc::mbar_arrive(bar_rempty(r));      // the raw slot may be refilled
-        if (++s == NS) { s = 0; ph ^= 1u; }
+        tc::mbar_arrive(bar_rempty(r));       // the row is in registers: the raw slot may be refilled
         if (++r == NR) { r = 0; rph ^= 1u; }
+        tc::mbar_wait(bar_aempty(sa), pha ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ta = tm_a + (uint32_t)(sa * 64) + lane_base;
+        tc::tmem_st32(ta, hi);
+        tc::tmem_st32(ta + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc::mbar_arrive(bar_afull(sa));
+        if (++sa == NA) { sa = 0; pha ^= 1u; }
       }
     }
   } else {
@@ -287,16 +327,15 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
       for (int k0 = 0; k0 < KT; k0 += a.drain) {
         tc::mbar_wait(bar_tfull(buf), tph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 2 * a.n_pad);
+        const uint32_t taddr = tm_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * a.n_pad);
 #pragma unroll
         for (int c0 = 0; c0 < kTcMaxN; c0 += 16) {
           if (c0 < a.n_pad) {
-            uint32_t v[16], u[16];
-            tc::tmem_ld16(taddr + (uint32_t)c0, v);                       // hi.hi partial
-            tc::tmem_ld16(taddr + (uint32_t)(a.n_pad + c0), u);            // cross terms
+            uint32_t v[16];
+            tc::tmem_ld16(taddr + (uint32_t)c0, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) z[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+            for (int j = 0; j < 16; ++j) z[c0 + j] += __uint_as_float(v[j]);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -921,13 +921,14 @@ static int tc_prepare(rfb_engine* e, const float* Sxy, int n_pix, int n_q, TcPla
   tp->n_pad = (n_q + 15) / 16 * 16;
   tp->k_tiles = (n_pix + kTcK - 1) / kTcK;
   const int kpad = tp->k_tiles * kTcK;
-  // TMEM: two sets of {hi.hi, cross terms} accumulators; a set is drained into registers every
-  // `drain` K tiles so that no accumulation chain exceeds 4 * drain truncating adds
-  tp->drain = 4;
+  // TMEM: two accumulators (drained into registers every `drain` K tiles so that no accumulation
+  // chain exceeds 12 * drain truncating adds) + two A stages of 32 hi + 32 lo columns
+  tp->drain = 2;
   tp->tmem_cols = 32;
-  while (tp->tmem_cols < 4 * tp->n_pad) tp->tmem_cols *= 2;
-  // shared memory: two MMA slots + as many raw A slots (HBM bytes in flight) as fit
-  tp->stages = 2;
+  while (tp->tmem_cols < 2 * tp->n_pad + 64 * kTcAStages) tp->tmem_cols *= 2;
+  if (tp->tmem_cols > 512) return RFB_OK;
+  // shared memory: B stages + as many raw A slots (HBM bytes in flight) as fit
+  tp->stages = 3;
   const size_t budget = 225 * 1024;
   const size_t fixed = 1024 + 512 + (size_t)tp->stages * tc_stage_bytes(tp->n_pad);
   if (fixed + 2 * kTcRawBytes > budget) return RFB_OK;
