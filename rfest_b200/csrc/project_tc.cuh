@@ -301,13 +301,15 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
           lo[4 * j + 2] = __float_as_uint(__uint_as_float(x2) - __uint_as_float(hi[4 * j + 2]));
           lo[4 * j + 3] = __float_as_uint(__uint_as_float(x3) - __uint_as_float(hi[4 * j + 3]));
         }
-        tc::mbar_arrive(bar_rempty(r));       // the row is in registers: the raw slot may be refilled
-        if (++r == NR) { r = 0; rph ^= 1u; }
         tc::mbar_wait(bar_aempty(sa), pha ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t ta = tm_a + (uint32_t)(sa * 64) + lane_base;
         tc::tmem_st32(ta, hi);
         tc::tmem_st32(ta + 32u, lo);
+        // the stores have consumed the registers the shared-memory loads filled, so the loads are
+        // complete: only now may the raw slot be handed back to the TMA producer
+        tc::mbar_arrive(bar_rempty(r));
+        if (++r == NR) { r = 0; rph ^= 1u; }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc::mbar_arrive(bar_afull(sa));
