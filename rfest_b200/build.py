@@ -6,6 +6,7 @@ nvcc cross-compiles without a GPU.  The shared object is git-ignored but travels
 to the GPU box with the repository snapshot.
 """
 
+import glob
 import os
 import shutil
 import subprocess
@@ -14,8 +15,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG_DIR, "csrc", "rfb_api.cu")
 LIB = os.path.join(PKG_DIR, "librfest_b200.so")
-HEADERS = [os.path.join(PKG_DIR, "csrc", h) for h in
-           ("common.cuh", "sweep.cuh", "update.cuh", "project.cuh")] + \
+HEADERS = sorted(glob.glob(os.path.join(PKG_DIR, "csrc", "*.cuh"))) + \
           [os.path.join(os.path.dirname(PKG_DIR), "include", "rfest_b200.h")]
 
 NVCC_FLAGS = [

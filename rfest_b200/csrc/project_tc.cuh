@@ -112,16 +112,45 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// low word of the shared-memory descriptor (start address in 16-byte units | leading-dim field); the
+// high word (stride 1024 B, version 1, SWIZZLE_128B) is the constant kDescHi
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
 // A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// Called by every lane of a converged warp; `elected` is non-zero in the one lane that issues.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t elected, uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo,
+                                            uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      ".reg .b64 bd;\n"
+      "mov.b64 bd, {%2, %5};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 e, %6, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(bdesc_lo), "r"(idesc), "r"(acc), "r"(kDescHi), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void commit_if(uint32_t elected, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "setp.ne.b32 e, %1, 0;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t e;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(e));
+  return e;
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -240,40 +269,45 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     }
   } else if (warp == 9) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = n_pad, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-      int sb = 0, sa = 0, buf = 0;
-      uint32_t phb = 0, pha = 0, tph = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int kt = 0; kt < KT; ++kt) {
-          const bool first = (kt % a.drain) == 0;          // first K tile into this accumulator
-          if (first) {
-            tc::mbar_wait(bar_tempty(buf), tph ^ 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          }
+    // The whole warp walks the loop with warp-uniform control flow and one elected lane issues: written
+    // as `if (lane == 0)` around the loop, every tcgen05 instruction got wrapped in a divergence-safe
+    // elect/retry sequence and the issuing thread itself (about 190 dependent instructions per K tile)
+    // paced the kernel.
+    // instruction descriptor: D fp32, A/B tf32, both K-major, N = n_pad, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+    const uint32_t blo_off = b_bytes >> 4;             // B_lo sits b_bytes behind B_hi (descriptor units of 16 B)
+    const uint32_t elected = tc::elect_one();
+    int sb = 0, sa = 0, buf = 0, dk = 0;
+    uint32_t phb = 0, pha = 0, tph = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const bool first = dk == 0;                      // first K tile into this accumulator
+        if (first) tc::mbar_wait(bar_tempty(buf), tph ^ 1u);
+        tc::mbar_wait(bar_afull(sa), pha);
+        tc::mbar_wait(bar_bfull(sb), phb);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool last = (++dk == a.drain) || kt == KT - 1;
+        {
           const uint32_t d = tm_acc + (uint32_t)(buf * a.n_pad);
-          tc::mbar_wait(bar_afull(sa), pha);
-          tc::mbar_wait(bar_bfull(sb), phb);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = tm_a + (uint32_t)(sa * 64), a_lo = a_hi + 32u;
+          const uint32_t bhi = tc::smem_desc_lo(st_bhi(sb)), blo = bhi + blo_off;
 #pragma unroll
           for (int ks = 0; ks < kTcK / 8; ++ks) {
-            const uint32_t off = (uint32_t)ks * 32u;       // 8 tf32 = 32 bytes along K inside the swizzle atom
-            const uint64_t bhi = tc::smem_desc(st_bhi(sb) + off), blo = tc::smem_desc(st_blo(sb) + off);
-            const uint32_t kc = (uint32_t)ks * 8u;          // 8 tensor-memory columns per k-step
-            tc::mma_tf32_ts(d, a_lo + kc, bhi, idesc, (first && ks == 0) ? 0u : 1u);
-            tc::mma_tf32_ts(d, a_hi + kc, blo, idesc, 1);
-            tc::mma_tf32_ts(d, a_hi + kc, bhi, idesc, 1);
+            // 8 tf32 = 32 bytes along K inside the swizzle atom = 2 descriptor units, 8 TMEM columns
+            const uint32_t ko = 2u * ks, kc = 8u * ks;
+            tc::mma_tf32_ts(elected, d, a_lo + kc, bhi + ko, idesc, (first && ks == 0) ? 0u : 1u);
+            tc::mma_tf32_ts(elected, d, a_hi + kc, blo + ko, idesc, 1);
+            tc::mma_tf32_ts(elected, d, a_hi + kc, bhi + ko, idesc, 1);
           }
-          tc::commit(bar_aempty(sa));        // stages reusable once these MMAs have read them
-          tc::commit(bar_bempty(sb));
-          if (++sa == NA) { sa = 0; pha ^= 1u; }
-          if (++sb == NS) { sb = 0; phb ^= 1u; }
-          if ((kt % a.drain) == a.drain - 1 || kt == KT - 1) {
-            tc::commit(bar_tfull(buf));      // partial sums complete
-            if (++buf == 2) { buf = 0; tph ^= 1u; }
-          }
+          tc::commit_if(elected, bar_aempty(sa));        // stages reusable once these MMAs have read them
+          tc::commit_if(elected, bar_bempty(sb));
+          if (last) tc::commit_if(elected, bar_tfull(buf));          // partial sums complete
+        }
+        if (++sa == NA) { sa = 0; pha ^= 1u; }
+        if (++sb == NS) { sb = 0; phb ^= 1u; }
+        if (last) {
+          dk = 0;
+          if (++buf == 2) { buf = 0; tph ^= 1u; }
         }
       }
     }

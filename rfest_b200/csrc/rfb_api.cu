@@ -933,6 +933,9 @@ static int tc_prepare(rfb_engine* e, const float* Sxy, int n_pix, int n_q, TcPla
   const size_t fixed = 1024 + 512 + (size_t)tp->stages * tc_stage_bytes(tp->n_pad);
   if (fixed + 2 * kTcRawBytes > budget) return RFB_OK;
   tp->n_raw = (int)std::min<size_t>(8, (budget - fixed) / kTcRawBytes);
+  if (const char* v = getenv("RFB_TC_NRAW")) tp->n_raw = std::max(2, std::min(tp->n_raw, atoi(v)));
+  if (const char* v = getenv("RFB_TC_DRAIN")) tp->drain = std::max(1, atoi(v));
+  if (const char* v = getenv("RFB_TC_STAGES")) tp->stages = std::max(2, std::min(tp->stages, atoi(v)));
   tp->smem = tc_smem_bytes(tp->n_pad, tp->stages, tp->n_raw);
   // hi = tf32 truncation of b, lo = b - hi (exact); transposed so that K is contiguous (K-major B)
   std::vector<float> h((size_t)2 * tp->n_pad * kpad, 0.f);
