@@ -190,6 +190,17 @@ int rfb_model_gram(rfb_model* m, int kind, double* gram, double* colsum, double*
  * `b` the full coefficient vector (no intercepts, as in the reference). */
 int rfb_model_filter_gram(rfb_model* m, int kind, int filter, const float* b, int weighted, double* gram);
 
+/* Confidence band of the predicted response (_get_response_variance, _glm.py:1166-1232).  For every
+ * filter f with data in `kind`: y_se_f[t] = sqrt(xs_t^T V_f xs_t) with V[f] the filter's coefficient
+ * covariance (host, float32 [n_coef x n_coef] row-major; NULL entry = width 0), then
+ *   pred  = out_nl(sum_f filter_nl(xs_t b_f + c_f)             + c_global)
+ *   upper = out_nl(sum_f filter_nl(xs_t b_f + c_f + 2 y_se_f)  + c_global)     lower: - 2 y_se_f
+ * (the reference's X_f w_f of the band lines equals XS_f b_f because w_f = S_f b_f, so the lagged
+ * matrix is not needed).  V has one entry per filter of the model.  pred / upper / lower receive this
+ * rank's n samples each: host pointers, or device pointers when on_device != 0. */
+int rfb_model_response_band(rfb_model* m, int kind, const float* b, const double* intercepts,
+                            const float* const* V, float* pred, float* upper, float* lower, int on_device);
+
 /* ---- fit loop (GLM.optimize, _glm.py:644-836) --------------------------------------------- */
 /* Prepare `max_iters` iterations from the current parameters with zeroed Adam state:
  *   step_sizes[max_iters]  per-iteration learning rate (a constant or a schedule evaluated

@@ -327,8 +327,7 @@ class OracleGLM:
 
     def initialize(self, y=None, num_subunits=1, dt=0.033, method="random", compute_ci=True,
                    random_seed=2046, verbose=0, add_noise_to_mle=False):
-        """_glm.py:395-436.  `compute_ci` covers `_get_filter_variance`; the response bands
-        (`_get_response_variance`) are out of scope."""
+        """_glm.py:395-436."""
         self.dt = dt
         self.init_method = method
         self.num_subunits = num_subunits
@@ -387,11 +386,16 @@ class OracleGLM:
         if len(self.y["train"]) == 0:
             raise ValueError("Training set is empty after burned in.")
         self.y_pred["mle"] = {"train": self.forwardpass(self.p["mle"], "train")}
+        if getattr(self, "compute_ci", None):                                # :521-524
+            self._get_filter_variance("mle")
+            self._get_response_variance("mle", "train")
         if y_dev is not None:
             self.y["dev"] = np.asarray(y_dev)[self.burn_in:]
             if len(self.y["dev"]) == 0:
                 raise ValueError("Dev set is empty after burned in.")
             self.y_pred["mle"]["dev"] = self.forwardpass(self.p["mle"], "dev")
+            if getattr(self, "compute_ci", None):                            # :532-533
+                self._get_response_variance("mle", "dev")
         self.mle_computed = True
 
     # ---- forward / cost / gradient ---------------------------------------
@@ -614,6 +618,37 @@ class OracleGLM:
                 w_se[name] = se
         self.V[w_type], self.b_se[w_type], self.w_se[w_type] = V, b_se, w_se
 
+    def _get_response_variance(self, w_type="opt", kind="train"):
+        """_glm.py:1166-1232.  Followed literally: the band lines use the raw lagged design
+        X @ w (:1205-1212) while the centre line uses XS @ b (:1187-1190)."""
+        self.y_pred_upper = getattr(self, "y_pred_upper", {})
+        self.y_pred_lower = getattr(self, "y_pred_lower", {})
+        X, XS = self.X[kind], self.XS.get(kind, None)
+        b, w, V = self.b[w_type], self.w[w_type], self.V[w_type]
+        icpt = self.intercept[w_type]
+        mid, up, lo = [], [], []
+        with np.errstate(over="ignore", invalid="ignore"):
+            for name in X:
+                if name in self.S:
+                    M = XS[name]
+                    y_se = np.sqrt(np.sum(M @ V[name].astype(M.dtype) * M, 1))          # :1186
+                    c = (M @ np.asarray(b[name], dtype=M.dtype)).reshape(-1) + self._scalar(icpt[name])
+                else:
+                    M = X[name]
+                    y_se = np.sqrt(np.sum(M @ V[name].astype(M.dtype) * M, 1))          # :1194-1196
+                    c = (M @ np.asarray(w[name], dtype=M.dtype)).reshape(-1) + self._scalar(icpt[name])
+                raw = (X[name] @ np.asarray(w[name], dtype=X[name].dtype)).reshape(-1) \
+                    + self._scalar(icpt[name])
+                nl = self.filter_nonlinearity[name]
+                mid.append(fnl(c, nl))
+                up.append(fnl(raw + 2 * y_se, nl))                                      # :1205-1208
+                lo.append(fnl(raw - 2 * y_se, nl))                                      # :1209-1212
+            g = self._scalar(icpt["global"])
+            out = self.output_nonlinearity
+            self.y_pred.setdefault(w_type, {})[kind] = fnl(np.array(mid).sum(0) + g, out)      # :1214-1218
+            self.y_pred_upper.setdefault(w_type, {})[kind] = fnl(np.array(up).sum(0) + g, out)
+            self.y_pred_lower.setdefault(w_type, {})[kind] = fnl(np.array(lo).sum(0) + g, out)
+
     def _extract_opt_params(self):
         """_glm.py:920-933."""
         self.b["opt"], self.w["opt"] = {}, {}
@@ -626,6 +661,9 @@ class OracleGLM:
         self.intercept["opt"] = self.p["opt"]["intercept"]
         if self.compute_ci:
             self._get_filter_variance("opt")
+            self._get_response_variance("opt", "train")                     # :934-937
+            if "dev" in self.y:
+                self._get_response_variance("opt", "dev")
 
     # ---- predict / score ---------------------------------------------------
     def predict(self, X, w_type="opt"):

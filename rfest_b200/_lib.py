@@ -69,6 +69,7 @@ SIGNATURES = {
     "rfb_model_value_and_grad": (_i, [_p, _i, _p, _p, _p, _p, _p]),
     "rfb_model_gram": (_i, [_p, _i, _p, _p, _p, _ip]),
     "rfb_model_filter_gram": (_i, [_p, _i, _i, _p, _i, _p]),
+    "rfb_model_response_band": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i]),
     "rfb_fit_begin": (_i, [_p, _i, _p, _d, _d, _i]),
     "rfb_fit_run": (_i, [_p, _i]),
     "rfb_fit_run_timed": (_i, [_p, _i, _dp]),

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "gram.cuh"
+#include "band.cuh"
 #include "project.cuh"
 #include "project_tc.cuh"
 #include "sweep.cuh"
@@ -1494,6 +1495,82 @@ extern "C" int rfb_model_filter_gram(rfb_model* m, int kind, int filter, const f
     d_w = ds.r_buf;
   }
   return gram_impl(m, kind, 4 * p.slot_chunk0[fl.slot], fl.n_coef, d_w, gram, nullptr, nullptr);
+}
+
+extern "C" int rfb_model_response_band(rfb_model* m, int kind, const float* b, const double* intercepts,
+                                       const float* const* V, float* pred, float* upper, float* lower,
+                                       int on_device) {
+  if (!m || !b || !intercepts || !V || !pred || !upper || !lower) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  DataSet& ds = m->data[kind];
+  if (!ds.bound) return fail(RFB_ERR_STATE, "no data bound for kind %d", kind);
+  TRY(ensure_plan(m));
+  const Plan& p = m->plan;
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  if (p.F > 2 * kMaxHeads) return fail(RFB_ERR_UNSUPPORTED, "response band: at most %d filters", 2 * kMaxHeads);
+  const size_t n = (size_t)ds.n;
+  // scratch: per filter lin + se, the three outputs when they go to the host, V and b images
+  size_t v_floats = 0;
+  for (int f = 0; f < p.F; ++f) v_floats += (size_t)m->filters[f].n_coef * m->filters[f].n_coef;
+  float *d_rows = nullptr, *d_small = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_small); cudaFree(d_out); };
+  CU(cudaMalloc(&d_rows, sizeof(float) * n * 2 * p.F));
+  if (cudaMalloc(&d_small, sizeof(float) * (v_floats + p.P + 4)) != cudaSuccess) { cleanup(); return fail(RFB_ERR_CUDA, "out of device memory"); }
+  if (!on_device && cudaMalloc(&d_out, sizeof(float) * n * 3) != cudaSuccess) { cleanup(); return fail(RFB_ERR_CUDA, "out of device memory"); }
+  float* d_b = d_small + v_floats;
+  cudaMemcpyAsync(d_b, b, sizeof(float) * p.P, cudaMemcpyHostToDevice, e->stream);
+  BandArgs ba{};
+  ba.n_rows = ds.n;
+  size_t v_off = 0;
+  for (int f = 0; f < p.F; ++f) {
+    const Filter& fl = m->filters[f];
+    const size_t pp = (size_t)fl.n_coef * fl.n_coef;
+    rfb_block* blk = fl.slot < ds.n_slots ? ds.blocks[fl.slot] : nullptr;
+    if (blk) {                                  // forwardpass only loops over self.X[kind]
+      const int i = ba.n_filters++;
+      QuadformArgs qa{};
+      qa.X = blk->d;
+      qa.ld = blk->ld;
+      qa.n_rows = ds.n;
+      qa.p = fl.n_coef;
+      qa.b = d_b + p.coef0[f];
+      qa.lin = d_rows + (size_t)(2 * i) * n;
+      qa.se = d_rows + (size_t)(2 * i + 1) * n;
+      const bool has_v = V[f] != nullptr;
+      if (has_v) cudaMemcpyAsync(d_small + v_off, V[f], sizeof(float) * pp, cudaMemcpyHostToDevice, e->stream);
+      else cudaMemsetAsync(d_small + v_off, 0, sizeof(float) * pp, e->stream);
+      qa.V = d_small + v_off;
+      if (ds.n > 0) {
+        quadform_kernel<<<(unsigned)((ds.n + kQfRows - 1) / kQfRows), 256, 0, e->stream>>>(qa);
+        e->launches++;
+      }
+      ba.lin[i] = qa.lin;
+      ba.se[i] = has_v ? qa.se : nullptr;
+      ba.icpt[i] = (float)intercepts[f];
+      ba.nl[i] = fl.nl;
+    }
+    v_off += pp;
+  }
+  ba.glob_icpt = (float)intercepts[p.F];
+  ba.out_nl = m->out_nl;
+  ba.pred = on_device ? pred : d_out;
+  ba.upper = on_device ? upper : d_out + n;
+  ba.lower = on_device ? lower : d_out + 2 * n;
+  if (ds.n > 0) {
+    band_combine_kernel<<<(unsigned)((ds.n + 255) / 256), 256, 0, e->stream>>>(ba);
+    e->launches++;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess && !on_device) {
+    cudaMemcpyAsync(pred, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(upper, d_out + n, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(lower, d_out + 2 * n, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cleanup();
+  if (ce != cudaSuccess) return fail(RFB_ERR_CUDA, "response band failed: %s", cudaGetErrorString(ce));
+  return RFB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -223,10 +223,20 @@ class DeviceVector:
         self.n = int(n)
         self.shape = (self.n,)
         self.dtype = np.dtype(np.float32)
-        self._block = Block(engine, (self.n + 3) // 4, 4)        # contiguous n floats (+ padding)
-        check(engine.lib.rfb_block_write(self._block.handle, 0, (self.n + 3) // 4,
-                                         C.c_void_p(int(device_ptr)), 1))
+        self._block = Block(engine, max(1, (self.n + 3) // 4), 4)   # contiguous n floats (+ padding)
+        if device_ptr is not None and self.n > 0:
+            check(engine.lib.rfb_block_write(self._block.handle, 0, (self.n + 3) // 4,
+                                             C.c_void_p(int(device_ptr)), 1))
         self._host = None
+
+    @classmethod
+    def empty(cls, engine, n):
+        """Uninitialised vector for a kernel to fill through `device_ptr`."""
+        return cls(engine, None, n)
+
+    @property
+    def device_ptr(self):
+        return self._block.device_ptr
 
     def __len__(self):
         return self.n
@@ -338,6 +348,20 @@ class DeviceModel:
             bb.ctypes.data_as(C.c_void_p) if bb is not None else None, int(bool(weighted)),
             G.ctypes.data_as(C.c_void_p)))
         return G
+
+    def response_band(self, kind, b, intercepts, V_list, n):
+        """-> (pred, upper, lower) DeviceVectors of this rank's n samples (rfb_model_response_band).
+        V_list holds one float32 [n_coef x n_coef] covariance (or None) per filter."""
+        bb = np.ascontiguousarray(b, dtype=np.float32)
+        ic = np.ascontiguousarray(intercepts, dtype=np.float64)
+        mats = [None if v is None else np.ascontiguousarray(v, dtype=np.float32) for v in V_list]
+        ptrs = (C.c_void_p * len(mats))(*[None if v is None else v.ctypes.data for v in mats])
+        out = [DeviceVector.empty(self.engine, n) for _ in range(3)]
+        check(self.lib.rfb_model_response_band(
+            self.handle, _lib.KIND[kind], bb.ctypes.data_as(C.c_void_p), ic.ctypes.data_as(C.c_void_p),
+            ptrs, C.c_void_p(out[0].device_ptr), C.c_void_p(out[1].device_ptr),
+            C.c_void_p(out[2].device_ptr), 1))
+        return tuple(out)
 
     # ---- fit loop ------------------------------------------------------------------------
     def fit_begin(self, step_sizes, alpha, beta, metric):

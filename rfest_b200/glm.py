@@ -351,8 +351,8 @@ class GLM:
     def initialize(self, y=None, num_subunits=1, dt=0.033, method="random", compute_ci=True,
                    random_seed=2046, verbose=0, add_noise_to_mle=False):
         """_glm.py:395-436.  `compute_ci` gives the coefficient covariances `V`, `b_se`, `w_se`
-        (`_get_filter_variance`); the response confidence bands of the reference
-        (`_get_response_variance`) need the n x prod(dims) lagged matrix and are not available."""
+        (`_get_filter_variance`) and the response confidence bands `y_pred_upper / y_pred_lower`
+        (`_get_response_variance`)."""
         self.dt = dt
         self.init_method = method
         self.num_subunits = num_subunits
@@ -437,10 +437,13 @@ class GLM:
         self.y_pred["mle"] = {"train": self.forwardpass(self.p["mle"], kind="train")}
         if self.compute_ci is None:
             self.compute_ci = compute_ci
-        if self.compute_ci:
+        if self.compute_ci:                                                       # _glm.py:521-524
             self._get_filter_variance(w_type="mle")
+            self._get_response_variance(w_type="mle", kind="train")
         if y_dev is not None:
             self.y_pred["mle"]["dev"] = self.forwardpass(self.p["mle"], kind="dev")
+            if self.compute_ci:                                                   # _glm.py:532-533
+                self._get_response_variance(w_type="mle", kind="dev")
         self.mle_computed = True
 
     def _get_filter_variance(self, w_type="opt"):
@@ -477,6 +480,29 @@ class GLM:
             else:
                 w_se[name] = se
         self.V[w_type], self.b_se[w_type], self.w_se[w_type] = V, b_se, w_se
+
+    def _get_response_variance(self, w_type="opt", kind="train"):
+        """_glm.py:1166-1232: prediction with its +/- 2 standard-error band.
+
+        y_se_f = sqrt(diag(XS_f V_f XS_f^T)) per filter; the band pushes XS_f b_f + c_f +/- 2 y_se_f
+        through the filter and output nonlinearities.  The reference writes the band's linear part
+        as X_f w_f with the n x prod(dims) lagged matrix; w_f = S_f b_f makes that XS_f b_f, which is
+        what the device kernel (csrc/band.cuh) uses.  Results stay in HBM (`DeviceVector`)."""
+        self._sync()
+        b_flat, ic = self._flatten(self.p[w_type])
+        V = self.V[w_type]
+        mats = [V.get(name) for name in self.filter_names]
+        pred, upper, lower = self._dm.response_band(kind, b_flat, ic, mats, self._n_local(kind))
+        self.y_pred.setdefault(w_type, {})[kind] = pred
+        self.y_pred_upper.setdefault(w_type, {})[kind] = upper
+        self.y_pred_lower.setdefault(w_type, {})[kind] = lower
+
+    def _n_local(self, kind):
+        """This rank's number of samples of `kind`."""
+        if kind in self._row_range:
+            lo, hi = self._row_range[kind]
+            return hi - lo
+        return self._n_trim[kind]
 
     # ------------------------------------------------------------------------------------
     # device model plumbing
@@ -805,8 +831,11 @@ class GLM:
             else:
                 self.w["opt"][name] = self.p["opt"][name]
         self.intercept["opt"] = self.p["opt"]["intercept"]
-        if self.compute_ci:                                                       # _glm.py:932-933
+        if self.compute_ci:                                                       # _glm.py:932-937
             self._get_filter_variance(w_type="opt")
+            self._get_response_variance(w_type="opt", kind="train")
+            if "dev" in self.y:
+                self._get_response_variance(w_type="opt", kind="dev")
 
     # ------------------------------------------------------------------------------------
     # prediction / scoring

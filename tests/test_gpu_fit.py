@@ -470,6 +470,59 @@ def test_filter_covariance_matches_oracle(distr, out_nl, filt_nl):
         assert abs(Wg - Wo) < 5e-3 * abs(Wo)
 
 
+@pytest.mark.parametrize("distr,out_nl,filt_nl,subunits", [("poisson", "softplus", "none", 1),
+                                                          ("gaussian", "none", "none", 1),
+                                                          ("poisson", "exponential", "softplus", 2)])
+def test_response_band_matches_oracle(distr, out_nl, filt_nl, subunits):
+    """compute_ci: y_pred / y_pred_upper / y_pred_lower of _get_response_variance (_glm.py:1166-1232) for
+    train and dev.  The oracle follows the reference literally (band lines from the raw lagged design
+    X @ w); the engine uses XS @ b."""
+    stim, y, _ = helpers.lnp_data(2600, (8, 5, 4), seed=23)
+    if distr == "gaussian":
+        y = (y - y.mean()).astype(np.float32)
+    n_tr = 2000
+    g, o = _pair(distr, out_nl)
+    for m in (g, o):
+        m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity=filt_nl,
+                            name="stimulus")
+        m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
+        m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.add_design_matrix(y[n_tr:], name="history", kind="dev")
+        m.initialize(num_subunits=subunits, method="random", random_seed=3)
+    _same_p0([o, g], scale=0.1)
+    if subunits > 1:            # distinct subunits
+        for k, name in enumerate(o.filter_names):
+            bump = (0.05 * np.random.default_rng(70 + k).standard_normal(np.asarray(o.p0[name]).shape)).astype(np.float32)
+            o.p0[name] = o.p0[name] + bump
+            g.p0[name] = (g.p0[name] + bump).astype(np.float32)
+    for m in (g, o):
+        m.fit(y={"train": y[:n_tr], "dev": y[n_tr:]}, num_iters=15, step_size=0.02, beta=0.01, verbose=0,
+              tolerance=0)
+    for kind in ("train", "dev"):
+        mid_o = np.asarray(o.y_pred["opt"][kind], dtype=np.float64)
+        up_o = np.asarray(o.y_pred_upper["opt"][kind], dtype=np.float64)
+        lo_o = np.asarray(o.y_pred_lower["opt"][kind], dtype=np.float64)
+        mid_g, up_g, lo_g = (np.asarray(d["opt"][kind], dtype=np.float64)
+                             for d in (g.y_pred, g.y_pred_upper, g.y_pred_lower))
+        assert mid_g.shape == mid_o.shape == up_g.shape == lo_g.shape
+        width = np.abs(up_o - lo_o).max()
+        assert width > 0
+        assert np.abs(mid_g - mid_o).max() < 1e-4 * max(1.0, np.abs(mid_o).max())
+        # the engine's own V (float64 Gram on the device) differs from the oracle's by ~1e-3 relative
+        assert np.abs(up_g - up_o).max() < 5e-3 * width + 1e-4 * np.abs(up_o).max()
+        assert np.abs(lo_g - lo_o).max() < 5e-3 * width + 1e-4 * np.abs(lo_o).max()
+    # with the oracle's covariances and parameters the band kernel itself is pinned tightly
+    g.V["opt"] = {k: np.asarray(v) for k, v in o.V["opt"].items()}
+    g.p["opt"] = {k: (dict(v) if k == "intercept" else np.asarray(v, dtype=np.float32)) for k, v in o.p["opt"].items()}
+    g._get_response_variance("opt", "train")
+    up_g = np.asarray(g.y_pred_upper["opt"]["train"], dtype=np.float64)
+    lo_g = np.asarray(g.y_pred_lower["opt"]["train"], dtype=np.float64)
+    up_o = np.asarray(o.y_pred_upper["opt"]["train"], dtype=np.float64)
+    lo_o = np.asarray(o.y_pred_lower["opt"]["train"], dtype=np.float64)
+    assert np.abs(up_g - up_o).max() < 1e-4 * np.abs(up_o).max()
+    assert np.abs(lo_g - lo_o).max() < 1e-4 * max(np.abs(lo_o).max(), np.abs(up_o).max())
+
+
 def test_generic_sweep_wide_design_without_basis():
     """A 3-D filter with no spline basis: the design is the raw lagged stimulus (1800 columns, beyond the
     register-resident kernels) -> generic fallback sweep."""

@@ -264,3 +264,31 @@ def test_trace_semantics():
         rp = m.forwardpass(m.all_params[i], "train")
         assert np.isclose(m.metric_train[i], m.compute_score(m.y["train"], rp, "r2"))
     assert np.array_equal(m.y_pred["opt"]["train"], m.forwardpass(m.all_params[-1], "train"))
+
+
+def test_response_band_restatement():
+    """_get_response_variance (_glm.py:1166-1232): the reference's band lines use the raw lagged design
+    X @ w, the centre line XS @ b.  w = S b makes them the same number -- the identity the engine's
+    lag-free band kernel rests on -- and a monotone nonlinearity orders lower <= centre <= upper."""
+    rng = np.random.default_rng(5)
+    n = 400
+    stim = rng.standard_normal((n, 4, 3))
+    y = rng.poisson(0.5, n).astype(np.float64)
+    m = OracleGLM(distr="poisson", output_nonlinearity="softplus", dtype=np.float64)
+    m.add_design_matrix(stim, dims=[6, 4, 3], df=[3, 3, 3], smooth="cr", name="stimulus")
+    m.add_design_matrix(y, dims=[5], df=[3], smooth="cr", shift=1, name="history")
+    m.initialize(method="random", random_seed=4, compute_ci=True)
+    m.fit(y=y, num_iters=10, step_size=0.05, beta=0.01, verbose=0)
+    for name in m.filter_names:
+        lin_raw = m.X["train"][name] @ m.w["opt"][name]
+        lin_xs = m.XS["train"][name] @ m.b["opt"][name]
+        assert np.abs(lin_raw - lin_xs).max() < 1e-12 * max(1.0, np.abs(lin_xs).max())
+        # the quadratic form behind y_se, written per row
+        V = m.V["opt"][name]
+        M = m.XS["train"][name]
+        q = np.einsum("ti,ij,tj->t", M, V, M)
+        assert np.allclose(np.sqrt(q), np.sqrt(np.sum(M @ V * M, 1)), rtol=1e-12)
+    mid, up, lo = (np.asarray(d["opt"]["train"]) for d in (m.y_pred, m.y_pred_upper, m.y_pred_lower))
+    assert mid.shape == up.shape == lo.shape == (n - 5,)
+    assert np.all(lo <= mid + 1e-12) and np.all(mid <= up + 1e-12) and np.any(up - lo > 1e-6)
+    assert np.allclose(mid, m.forwardpass(m.p["opt"], "train"))
