@@ -684,7 +684,10 @@ class OracleGLM:
                     self.XS["test"][name] = self.XS["test"]["stimulus"]
             self.X["test"].pop("stimulus")
             self.XS["test"].pop("stimulus")
-        return self.forwardpass(p, "test")
+        y_pred = self.forwardpass(p, "test")
+        if self.compute_ci:                                                 # :991-993
+            self._get_response_variance(w_type, "test")
+        return y_pred
 
     def score(self, X_test, y_test, metric="corrcoef", w_type="opt", return_prediction=False):
         """_glm.py:1015-1056."""

@@ -863,7 +863,10 @@ class GLM:
                 store["test"].pop("stimulus")
         self.y.pop("test", None)
         self._dirty = True
-        return self.forwardpass(p, kind="test")
+        y_pred = self.forwardpass(p, kind="test")
+        if self.compute_ci and w_type in self.V:                                 # _glm.py:991-993
+            self._get_response_variance(w_type=w_type, kind="test")
+        return y_pred
 
     @staticmethod
     def compute_score(y, y_pred, metric):

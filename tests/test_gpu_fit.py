@@ -523,6 +523,52 @@ def test_response_band_matches_oracle(distr, out_nl, filt_nl, subunits):
     assert np.abs(lo_g - lo_o).max() < 1e-4 * max(np.abs(lo_o).max(), np.abs(up_o).max())
 
 
+def test_permutation_test_and_significance():
+    """rfest/check.py:24-53 (stimulus permutation test: n_perm x (projection + forward pass) of the test
+    set) and :103-126 (Wald test), against the same procedure run on the oracle; and the test-set
+    confidence band predict() leaves behind (_glm.py:991-993)."""
+    from rfest_b200 import check
+
+    stim, y, _ = helpers.lnp_data(3000, (8, 5, 4), seed=29)
+    n_tr = 2200
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", name="stimulus")
+        m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(method="random", random_seed=3)
+    _same_p0([o, g], scale=0.1)
+    for m in (g, o):
+        m.fit(y=y[:n_tr], num_iters=40, step_size=0.03, beta=0.01, verbose=0, tolerance=0)
+    X_test, y_test = stim[n_tr:], y[n_tr:]
+
+    np.random.seed(7)
+    true_g, perm_g = check.compute_permutation_test(g, X_test, y_test, n_perm=6)
+    np.random.seed(7)
+    true_o = o.score({"stimulus": X_test, "history": y_test}, y_test)
+    perm_o = np.array([o.score({"stimulus": X_test[np.random.permutation(np.arange(len(X_test)))],
+                                "history": y_test}, y_test) for _ in range(6)])
+    assert abs(true_g - true_o) < 2e-4
+    assert np.abs(perm_g - perm_o).max() < 2e-4
+    assert g.compute_ci                                   # restored after the shuffles
+
+    Wg, pg = check.significance(g)
+    for name in o.filter_names:
+        po = np.asarray(o.p["opt"][name], dtype=np.float64)
+        Wo = float(np.squeeze(po.T @ np.linalg.inv(o.V["opt"][name]) @ po))
+        assert abs(float(Wg[name]) - Wo) < 5e-3 * abs(Wo)
+        assert 0.0 <= pg[name] <= 1.0
+
+    g.predict({"stimulus": X_test, "history": y_test})
+    o.predict({"stimulus": X_test, "history": y_test})
+    for d_g, d_o in ((g.y_pred, o.y_pred), (g.y_pred_upper, o.y_pred_upper), (g.y_pred_lower, o.y_pred_lower)):
+        a, b = np.asarray(d_g["opt"]["test"], dtype=np.float64), np.asarray(d_o["opt"]["test"], dtype=np.float64)
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() < 5e-3 * np.abs(b).max()
+    r = np.asarray(g.y_pred["opt"]["test"])
+    assert np.isfinite(check.residuals_pearson(y_test[7:], r)).all()
+    assert np.isfinite(check.residuals_deviance(y_test[7:], r)).all()
+
+
 def test_generic_sweep_wide_design_without_basis():
     """A 3-D filter with no spline basis: the design is the raw lagged stimulus (1800 columns, beyond the
     register-resident kernels) -> generic fallback sweep."""
