@@ -1433,8 +1433,9 @@ static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float*
   a.ncols = ncols;
   a.n_tiles = (ncols + kGramTile - 1) / kGramTile;
   a.n_pairs = a.n_tiles * (a.n_tiles + 1) / 2;
-  // enough slabs to fill the chip about twice, but never shorter than 4096 rows
-  int slabs = std::max(1, (2 * e->num_sms + a.n_pairs - 1) / a.n_pairs);
+  // row slabs: about four balanced waves of CTAs (4 resident per SM: 206 registers x 64 threads), never shorter than 4096 rows
+  const int resident = 4 * e->num_sms;
+  int slabs = std::max(1, (4 * resident) / a.n_pairs);
   slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, ds.n / 4096));
   a.n_slabs = slabs;
   const size_t n_entries = (size_t)ncols * ncols + 2 * (size_t)ncols;
@@ -1442,7 +1443,12 @@ static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float*
   CU(cudaMalloc(&d_part, sizeof(double) * n_entries * slabs));
   CU(cudaMalloc(&d_out, sizeof(double) * n_entries));
   a.part = d_part;
-  gram_kernel<<<dim3(a.n_pairs, slabs), 256, 0, e->stream>>>(a);
+  static bool gram_attr = false;
+  if (!gram_attr) {
+    CU(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmem));
+    gram_attr = true;
+  }
+  gram_kernel<<<dim3(a.n_pairs, slabs), kGramThreads, kGramSmem, e->stream>>>(a);
   gram_reduce_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, e->stream>>>(d_part, slabs, (long long)n_entries, d_out);
   e->launches += 2;
   cudaError_t ce = cudaGetLastError();
