@@ -46,6 +46,8 @@ extern "C" {
 #define RFB_NL_TANH 4
 #define RFB_NL_RELU 5        /* where(x > 0, x, 1e-7) (_glm.py:152-157)                  */
 #define RFB_NL_LEAKY_RELU 6
+#define RFB_NL_SOFTMAX 7      /* exp(x) / sum over ALL samples of exp(x) (_glm.py:134-140); as the
+                                output nonlinearity only: two sweeps per evaluation           */
 
 /* noise distribution: GLM.cost, rfest/GLM/_glm.py:598-603 */
 #define RFB_DISTR_GAUSSIAN 0 /* loss_mse, rfest/loss.py:14-16       */

@@ -15,7 +15,7 @@ ABI_VERSION = 1
 OK = 0
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_STATE = -1, -2, -3, -4, -5
 NL = {"none": 0, "softplus": 1, "exponential": 2, "sigmoid": 3, "tanh": 4, "relu": 5,
-      "leaky_relu": 6}
+      "leaky_relu": 6, "softmax": 7}
 DISTR = {"gaussian": 0, "poisson": 1}
 KIND = {"train": 0, "dev": 1, "test": 2}
 METRIC = {None: 0, "mse": 1, "r2": 2, "corrcoef": 3}

@@ -49,6 +49,7 @@ struct SweepArgs {
   float* r_out;                     // optional [n_rows]
   int flush_tiles;                  // fp32 -> fp64 flush cadence, in tiles
   int n_stages;                     // staged variant: depth of each warp's copy ring
+  const float* softmax;             // out_nl == RFB_NL_SOFTMAX: {1 / Z, D} on the device (see softmax_scale)
 };
 
 // One-shot exchange over NVLink peer memory (multi-GPU): every rank owns a buffer

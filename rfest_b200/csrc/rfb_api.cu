@@ -19,6 +19,7 @@
 #include "project.cuh"
 #include "project_tc.cuh"
 #include "sweep.cuh"
+#include "softmax.cuh"
 #include "update.cuh"
 
 using namespace rfb;
@@ -243,6 +244,10 @@ struct rfb_model {
   bool have_params = false;
   SweepBuffers sb[3];
   double* fin_eval = nullptr;
+  // output softmax: per data set {Z, sum (dL/dr) r, sum r} (double), block partials, {1 / Z, D} (float)
+  double* sm_scal[3] = {};
+  double* sm_part[3] = {};
+  float* sm_f[3] = {};
   Fit fit;
 };
 
@@ -531,7 +536,7 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
 // Launch one sweep over data set `kind` with the parameter image `ps`.  Leaves the per-CTA
 // partial sums in m->sb[kind].cta_part (grid rows).
 static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* head_nl, bool bwd,
-                        float* r_out) {
+                        float* r_out, int out_nl_override = -1, const float* softmax = nullptr) {
   const Plan& p = m->plan;
   DataSet& ds = m->data[kind];
   rfb_engine* e = m->e;
@@ -562,7 +567,8 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
     a.head_nl[h] = h < p.Ht ? head_nl[h] : RFB_NL_NONE;
     a.head_slotmask[h] = h < p.Ht ? p.head_slotmask[h] : 0u;
   }
-  a.out_nl = m->out_nl;
+  a.out_nl = out_nl_override >= 0 ? out_nl_override : m->out_nl;
+  a.softmax = softmax;
   a.distr = m->distr;
   a.two_over_n = ds.n_total > 0 ? (float)(2.0 / ds.n_total) : 0.f;
   a.warp_acc = sb.warp_acc;
@@ -596,6 +602,46 @@ static int launch_reduce(rfb_model* m, int kind0, int e0, int n0, double* out0, 
   }
   reduce_partials_kernel<<<blocks0 + blocks1, dim3(kReduceEx, kReduceEy), 0, m->e->stream>>>(s0, s1, blocks0);
   m->e->launches++;
+  CU(cudaGetLastError());
+  return RFB_OK;
+}
+
+// ---- output softmax (see softmax.cuh) ------------------------------------------------------------
+static int allreduce_device_f64(rfb_engine* e, double* d, size_t count);
+// Scratch of the softmax evaluation of data set `kind`; allocation is not capturable, so the fit
+// calls this before it captures the iteration.
+static int ensure_softmax_buffers(rfb_model* m, int kind) {
+  DataSet& ds = m->data[kind];
+  if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * ((size_t)ds.n + 4)));
+  if (!m->sm_scal[kind]) {
+    CU(cudaMalloc(&m->sm_scal[kind], sizeof(double) * 3));
+    CU(cudaMalloc(&m->sm_part[kind], sizeof(double) * 2 * kSoftmaxBlocks));
+    CU(cudaMalloc(&m->sm_f[kind], sizeof(float) * 2));
+  }
+  return RFB_OK;
+}
+
+// Enqueue steps 1-2 of the softmax evaluation at parameters `ps`; afterwards m->sm_f[kind] holds
+// {1 / Z, D} for the final sweep.  `want_d`: the gradient follows (needs the response).
+static int softmax_prepare(rfb_model* m, int kind, const ParamSet& ps, const int* head_nl, bool want_d) {
+  DataSet& ds = m->data[kind];
+  rfb_engine* e = m->e;
+  const Plan& p = m->plan;
+  double* Z = m->sm_scal[kind];
+  double* D = m->sm_scal[kind] + 1;
+  TRY(launch_sweep(m, kind, ps, head_nl, false, ds.r_buf, RFB_NL_EXPONENTIAL));
+  TRY(launch_reduce(m, kind, p.Ht * p.ctot + S_R, 1, Z, -1, 0, 0, nullptr));
+  TRY(allreduce_device_f64(e, Z, 1));
+  if (want_d) {
+    softmax_stats_kernel<<<kSoftmaxBlocks, 256, 0, e->stream>>>(
+        ds.r_buf, ds.y, ds.n, Z, m->distr, ds.n_total > 0 ? (float)(2.0 / ds.n_total) : 0.f, m->sm_part[kind]);
+    softmax_sum_kernel<<<1, 32, 0, e->stream>>>(m->sm_part[kind], kSoftmaxBlocks, D);
+    e->launches += 2;
+    CU(cudaGetLastError());
+    TRY(allreduce_device_f64(e, D, 2));
+  }
+  softmax_finish_kernel<<<1, 32, 0, e->stream>>>(Z, want_d ? D : nullptr, m->sm_f[kind]);
+  e->launches++;
   CU(cudaGetLastError());
   return RFB_OK;
 }
@@ -1138,7 +1184,8 @@ extern "C" int rfb_model_create(rfb_engine* e, int distr, int output_nl, rfb_mod
   if (!e || !out) return fail(RFB_ERR_INVALID, "NULL argument");
   if (distr != RFB_DISTR_GAUSSIAN && distr != RFB_DISTR_POISSON)
     return fail(RFB_ERR_UNSUPPORTED, "unknown distribution %d", distr);
-  if (!valid_nl(output_nl)) return fail(RFB_ERR_UNSUPPORTED, "unknown output nonlinearity %d", output_nl);
+  if (!valid_nl(output_nl) && output_nl != RFB_NL_SOFTMAX)
+    return fail(RFB_ERR_UNSUPPORTED, "unknown output nonlinearity %d", output_nl);
   rfb_model* m = new rfb_model();
   m->e = e;
   m->distr = distr;
@@ -1168,6 +1215,11 @@ extern "C" int rfb_model_destroy(rfb_model* m) {
     cudaFree(ds.y);
     cudaFree(ds.r_buf);
   }
+  for (int k = 0; k < 3; ++k) {
+    cudaFree(m->sm_scal[k]);
+    cudaFree(m->sm_part[k]);
+    cudaFree(m->sm_f[k]);
+  }
   delete m;
   return RFB_OK;
 }
@@ -1187,6 +1239,8 @@ extern "C" int rfb_model_clear_filters(rfb_model* m) {
 extern "C" int rfb_model_add_filter(rfb_model* m, int slot, int filter_nl, int n_coef) {
   if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
   if (slot < 0 || slot >= kMaxSlots) return fail(RFB_ERR_UNSUPPORTED, "slot %d out of range (max %d)", slot, kMaxSlots);
+  if (filter_nl == RFB_NL_SOFTMAX)
+    return fail(RFB_ERR_UNSUPPORTED, "softmax is available as the output nonlinearity only");
   if (!valid_nl(filter_nl)) return fail(RFB_ERR_UNSUPPORTED, "unknown filter nonlinearity %d", filter_nl);
   if (n_coef < 1) return fail(RFB_ERR_INVALID, "filter needs at least one coefficient");
   if (m->fit.active) return fail(RFB_ERR_STATE, "cannot add filters during a fit");
@@ -1362,7 +1416,14 @@ static int eval_impl(rfb_model* m, int kind, const float* b, const double* inter
   }
   const bool want_grad = grad_b != nullptr || grad_ic != nullptr;
   if (want_grad && !ds.has_y) return fail(RFB_ERR_STATE, "a gradient needs the response of kind %d", kind);
-  TRY(launch_sweep(m, kind, m->tmp, head_nl.data(), want_grad, d_r));
+  const float* d_sm = nullptr;
+  if (m->out_nl == RFB_NL_SOFTMAX) {
+    TRY(ensure_softmax_buffers(m, kind));
+    if (d_r) d_r = ds.r_buf;
+    TRY(softmax_prepare(m, kind, m->tmp, head_nl.data(), want_grad));
+    d_sm = m->sm_f[kind];
+  }
+  TRY(launch_sweep(m, kind, m->tmp, head_nl.data(), want_grad, d_r, -1, d_sm));
   const int tail = p.Ht * p.ctot;
   double* d_sc = m->fin_eval + (want_grad ? tail : 0);
   std::vector<double> fin;
@@ -1609,10 +1670,17 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   Fit& f = m->fit;
   const Plan& p = m->plan;
   rfb_engine* e = m->e;
+  const bool softmax = m->out_nl == RFB_NL_SOFTMAX;
   if (ev) CU(cudaEventRecord(ev[0], e->stream));
-  TRY(launch_sweep(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only, r_train));
+  if (softmax) TRY(softmax_prepare(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only));
+  TRY(launch_sweep(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only, r_train, -1,
+                   softmax ? m->sm_f[RFB_KIND_TRAIN] : nullptr));
   if (ev) CU(cudaEventRecord(ev[1], e->stream));
-  if (f.has_dev) TRY(launch_sweep(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false, r_dev));
+  if (f.has_dev) {
+    if (softmax) TRY(softmax_prepare(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false));
+    TRY(launch_sweep(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false, r_dev, -1,
+                     softmax ? m->sm_f[RFB_KIND_DEV] : nullptr));
+  }
   if (ev) CU(cudaEventRecord(ev[2], e->stream));
   const int tail = p.Ht * p.ctot;
   const bool xchg = e->comm && e->use_xchg && e->xchg_ready && (long long)p.NE + kNumScalars <= e->xchg_cap;
@@ -1735,6 +1803,10 @@ extern "C" int rfb_fit_begin(rfb_model* m, int max_iters, const double* step_siz
   // size the sweeps' scratch outside the capture (allocation is not capturable)
   TRY(ensure_sweep_buffers(m, RFB_KIND_TRAIN));
   if (f.has_dev) TRY(ensure_sweep_buffers(m, RFB_KIND_DEV));
+  if (m->out_nl == RFB_NL_SOFTMAX) {
+    TRY(ensure_softmax_buffers(m, RFB_KIND_TRAIN));
+    if (f.has_dev) TRY(ensure_softmax_buffers(m, RFB_KIND_DEV));
+  }
   CU(cudaStreamSynchronize(e->stream));
 
   const int64_t l0 = e->launches;

@@ -61,6 +61,7 @@ __device__ __forceinline__ void nl_eval(int kind, float x, float& f, float& d) {
       d = (e > 1e30f) ? 1.0f : fast_div(e, s);
       break;
     }
+    case RFB_NL_SOFTMAX:        // exp(x) here; the epilogues divide by the global sum (softmax_fix)
     case RFB_NL_EXPONENTIAL: {
       const float e = expf(x);
       f = e;
@@ -141,6 +142,22 @@ __host__ __device__ inline size_t sweep_smem_bytes(int warps, int stages, int RB
   return (size_t)warps * stages * (sweep_stage_bytes(RB, ctot) + sizeof(unsigned long long));
 }
 
+// Output softmax over all samples (GLM.fnl 'softmax', _glm.py:134-140): r_t = exp(u_t) / Z with
+// Z = sum_s exp(u_s) over every sample of the data set (all ranks).  Z is produced by a first
+// forward sweep with the exponential in its place; a.softmax = {1 / Z, D} with
+// D = sum_s (dL/dr_s) r_s, so that  dL/du_t = r_t (dL/dr_t - D)  (the softmax Jacobian applied to the
+// loss cotangent).  sum_t dL/du_t vanishes identically (the output does not depend on a shift of u), so
+// the gradients of the global intercept and of the intercepts of 'none' filters are reported as exactly 0
+// rather than as rounding noise, which Adam would normalise into a random walk of step_size per iteration.
+__device__ __forceinline__ void softmax_scale(const SweepArgs& a, int out_kind, float& r) {
+  if (out_kind == RFB_NL_SOFTMAX) r *= __ldg(a.softmax);
+}
+__device__ __forceinline__ float softmax_delta(const SweepArgs& a, int out_kind, float delta, float r, float dldr,
+                                               bool rowok) {
+  if (out_kind != RFB_NL_SOFTMAX) return delta;
+  return rowok ? r * (dldr - __ldg(a.softmax + 1)) : 0.f;
+}
+
 // ---- per-row epilogue shared by both variants: nonlinearities, loss terms, delta -------------------
 // `tot[h]` = this lane's row's dot products.  Fills r, delta-scaled head derivatives dh[] and adds
 // the row's terms to the fp32 scalar partials when `count`.
@@ -166,6 +183,7 @@ __device__ __forceinline__ void row_epilogue(const SweepArgs& a, const float (&t
   u += gic;
   float r, dr;
   nl_eval(out_kind, u, r, dr);
+  if (SPEC == 0) softmax_scale(a, out_kind, r);
   float la, lb, dldr;
   const float err = yv - r;
   if (poisson) {                                   // rfest/loss.py:4-11
@@ -182,6 +200,7 @@ __device__ __forceinline__ void row_epilogue(const SweepArgs& a, const float (&t
     dldr = -err * a.two_over_n;
   }
   float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
+  if (SPEC == 0) delta = softmax_delta(a, out_kind, delta, r, dldr, rowok);
   if (count) {
     sc[S_LOSS_A] += la;
     sc[S_LOSS_B] += lb;
@@ -189,12 +208,12 @@ __device__ __forceinline__ void row_epilogue(const SweepArgs& a, const float (&t
     sc[S_RR] += r * r;
     sc[S_YR] += yv * r;
     sc[S_SQERR] += err * err;
-    sc[S_GGLOBAL] += delta;
+    if (SPEC != 0 || out_kind != RFB_NL_SOFTMAX) sc[S_GGLOBAL] += delta;
   }
 #pragma unroll
   for (int h = 0; h < H; ++h) {
     dh[h] = (delta == 0.f) ? 0.f : delta * dh[h];
-    if (count) sc[S_GHEAD + h] += dh[h];
+    if (count && !(SPEC == 0 && out_kind == RFB_NL_SOFTMAX && a.head_nl[h] == RFB_NL_NONE)) sc[S_GHEAD + h] += dh[h];
   }
   r_out = r;
 }
@@ -219,6 +238,7 @@ __device__ __forceinline__ void multihead_epilogue(const SweepArgs& a, float tot
   u += gic;
   float r, dr;
   nl_eval(a.out_nl, u, r, dr);
+  softmax_scale(a, a.out_nl, r);
   float la, lb, dldr;
   const float err = yv - r;
   if (poisson) {                                   // rfest/loss.py:4-11
@@ -234,7 +254,7 @@ __device__ __forceinline__ void multihead_epilogue(const SweepArgs& a, float tot
     lb = 0.f;
     dldr = -err * a.two_over_n;
   }
-  const float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
+  const float delta = softmax_delta(a, a.out_nl, (dldr == 0.f || !rowok) ? 0.f : dldr * dr, r, dldr, rowok);
   if (rowok && lane < RB) {
     sc[S_LOSS_A] += la;
     sc[S_LOSS_B] += lb;
@@ -242,10 +262,10 @@ __device__ __forceinline__ void multihead_epilogue(const SweepArgs& a, float tot
     sc[S_RR] += r * r;
     sc[S_YR] += yv * r;
     sc[S_SQERR] += err * err;
-    sc[S_GGLOBAL] += delta;
+    if (a.out_nl != RFB_NL_SOFTMAX) sc[S_GGLOBAL] += delta;
   }
   delta_hr = (delta == 0.f || !lane_valid) ? 0.f : delta * dphi;
-  if (lane < H * RB) sc_head += delta_hr;
+  if (lane < H * RB && !(a.out_nl == RFB_NL_SOFTMAX && kind_lane == RFB_NL_NONE)) sc_head += delta_hr;
   r_out = r;
 }
 
@@ -789,6 +809,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
       u += gic;
       float rr, dr;
       nl_eval(a.out_nl, u, rr, dr);
+      softmax_scale(a, a.out_nl, rr);
       const long long row = row0 + r;
       const bool rowok = row < a.n_rows;
       const float yv = (rowok && a.y != nullptr) ? __ldg(a.y + row) : 0.f;
@@ -807,14 +828,15 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
         lb = 0.f;
         dldr = -err * a.two_over_n;
       }
-      const float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
+      const float delta = softmax_delta(a, a.out_nl, (dldr == 0.f || !rowok) ? 0.f : dldr * dr, rr, dldr, rowok);
       if (rowok && lane == 0) {
         sc[S_LOSS_A] += la; sc[S_LOSS_B] += lb; sc[S_R] += rr; sc[S_RR] += rr * rr;
-        sc[S_YR] += yv * rr; sc[S_SQERR] += err * err; sc[S_GGLOBAL] += delta;
+        sc[S_YR] += yv * rr; sc[S_SQERR] += err * err;
+        if (a.out_nl != RFB_NL_SOFTMAX) sc[S_GGLOBAL] += delta;
         if (a.r_out != nullptr) a.r_out[row] = rr;
       }
       delta_h[r] = (delta == 0.f || lane >= H) ? 0.f : delta * dphi;
-      sc_head += (double)delta_h[r];
+      if (!(a.out_nl == RFB_NL_SOFTMAX && kind_lane == RFB_NL_NONE)) sc_head += (double)delta_h[r];
     }
     // pass 2: gradient of the tile, added once per chunk into the fp64 accumulator row.  The delta
     // broadcasts happen before the (lane-divergent) chunk loop: no shuffles inside it.

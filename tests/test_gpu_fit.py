@@ -569,6 +569,54 @@ def test_permutation_test_and_significance():
     assert np.isfinite(check.residuals_deviance(y_test[7:], r)).all()
 
 
+@pytest.mark.parametrize("distr,filt_nl,subunits,dev", [("poisson", "none", 1, True), ("gaussian", "none", 1, False),
+                                                       ("poisson", "softplus", 2, True)])
+def test_softmax_output_matches_oracle(distr, filt_nl, subunits, dev):
+    """output_nonlinearity='softmax' (GLM.fnl, _glm.py:134-140): r = exp(u) / sum over ALL samples.  The
+    engine evaluates it with a first sweep for the normaliser, a vector pass for the Jacobian scalar and
+    the ordinary sweep (csrc/softmax.cuh); losses, gradients and the whole fit must follow the oracle."""
+    n = 2400
+    stim, y, _ = helpers.lnp_data(n, (8, 5, 4), seed=37)
+    y = (y / max(1.0, y.sum())).astype(np.float32) if distr == "gaussian" else y
+    n_tr = 1800 if dev else n
+    g, o = _pair(distr, "softmax")
+    for m in (g, o):
+        m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity=filt_nl,
+                            name="stimulus")
+        m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        if dev:
+            m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
+            m.add_design_matrix(y[n_tr:], name="history", kind="dev")
+        m.initialize(num_subunits=subunits, method="random", random_seed=3, compute_ci=False)
+    _same_p0([o, g], scale=0.1, icpt=0.02)
+    if subunits > 1:
+        for k, name in enumerate(o.filter_names):
+            bump = (0.05 * np.random.default_rng(40 + k).standard_normal(np.asarray(o.p0[name]).shape)).astype(np.float32)
+            o.p0[name] = o.p0[name] + bump
+            g.p0[name] = (g.p0[name] + bump).astype(np.float32)
+    fit_y = {"train": y[:n_tr]}
+    if dev:
+        fit_y["dev"] = y[n_tr:]
+    # value and gradient at p0
+    for m in (g, o):
+        m.y["train"] = np.asarray(y[:n_tr])[m.burn_in:].astype(m.dtype)
+        m.alpha, m.beta = 1.0, 0.01
+    g._dirty = True
+    vg, gg = g.value_and_grad(g.p0, "train")
+    vo, go = o.value_and_grad(o.p0, "train")
+    assert abs(vg - vo) < 1e-5 * abs(vo)
+    for name in o.filter_names:
+        scale = max(np.abs(go[name]).max(), 1e-12)
+        assert np.abs(gg[name] - go[name]).max() < 5e-4 * scale
+    r_g = np.asarray(g.forwardpass(g.p0, "train"), dtype=np.float64)
+    assert abs(r_g.sum() - 1.0) < 1e-4                       # a distribution over the samples
+    for m in (g, o):
+        # (Gaussian: responses of size 1/n make the MSE ~1e-7, so no penalty there -- it would be the whole cost)
+        m.fit(y=fit_y, num_iters=40, alpha=1.0, beta=0.01 if distr == "poisson" else 0.0, metric="corrcoef",
+              step_size=0.02 if distr == "poisson" else 0.005, tolerance=0, verbose=0)
+    _compare_fit(g, o, dev)
+
+
 def test_generic_sweep_wide_design_without_basis():
     """A 3-D filter with no spline basis: the design is the raw lagged stimulus (1800 columns, beyond the
     register-resident kernels) -> generic fallback sweep."""
