@@ -134,12 +134,117 @@ __global__ void __launch_bounds__(128) temporal_project_kernel(const TemporalArg
   }
 }
 
-// Faster variant for nlag <= 64: the temporal basis sits in constant memory (padded with zero rows
-// to a multiple of 8 lags, so FFMAs take it as an operand through the constant cache), and the lag
-// loop is unrolled by 8 over a 15-value register window of Z, of which only 8 values are new per
-// step: one global load per 64 FMAs instead of 16.
+// Faster variant for nlag <= 64: the temporal basis sits in constant memory (zero rows past nlag), and the
+// lag loop is unrolled by 8 over a 15-value register window of Z, of which only 8 values are new per
+// step: one global load per 64 FMAs instead of 16.  A thread whose whole window of raw rows is held in Z
+// (all but the first and last few of a recording) takes the FAST path: no bounds checks, one pointer
+// walking down Z's column -- in the first version a quarter of all instructions were the 64-bit index
+// arithmetic and range tests of the loads.  Both paths add the lags in the same order, so results do not
+// depend on which one a row takes (sharded == unsharded bit for bit).  The last, partial step of 8 lags
+// only issues the lags that exist, and the 8 values a step adds to the window are loaded one step ahead.
 constexpr int kTempMaxLag = 64;
 __constant__ float c_st[kTempMaxLag * 16];
+
+// Packed arithmetic: the accumulators of two neighbouring basis columns (d, d + 1) share a 64-bit register
+// pair and are updated by one fma.rn.f32x2 (SASS FFMA2) -- two IEEE fused multiply-adds, bit-identical to the
+// scalar ones, for one issue slot.  The kernel was issue-bound (65 % of its instructions were FFMAs at 75 %
+// issue utilisation); halving the FMA instructions puts it on the FMA pipe itself.
+typedef unsigned long long u64_t;
+__device__ __forceinline__ u64_t pack2(float lo, float hi) {
+  u64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64_t ffma2(u64_t a, u64_t b, u64_t c) {
+  u64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+template <int DFT, bool FAST>
+__device__ __forceinline__ void temporal_accumulate(const TemporalArgs& a, long long src0, int q, float (&acc)[8][DFT]) {
+  constexpr int TT = 8;
+  constexpr bool PACKED = (DFT % 2) == 0;
+  constexpr int DP = PACKED ? DFT / 2 : 1;
+  const float* zp = nullptr;
+  const long long ldz = a.ldz;
+  if (FAST) zp = a.Z + (src0 - a.z_src0) * ldz + q;
+  auto zload = [&](int k) -> float {                // raw row src0 + k of column q
+    if (FAST) return __ldg(zp + k * ldz);
+    const long long src = src0 + k;
+    if (src < 0 || src >= a.n_raw_total) return 0.f;
+    const long long zr = src - a.z_src0;
+    return (zr >= 0 && zr < a.n_z) ? __ldg(a.Z + zr * ldz + q) : 0.f;
+  };
+  u64_t acc2[TT][DP];
+  if (PACKED) {
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+      for (int dp = 0; dp < DP; ++dp) acc2[tt][dp] = 0ull;
+  }
+  // one lag: acc[tt][:] += w[tt + j] * st[j][:]
+  auto lag = [&](const float (&w)[2 * TT - 1], const float* cs, int j) {
+    if (PACKED) {
+      u64_t ww[TT];
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt) ww[tt] = pack2(w[tt + j], w[tt + j]);
+#pragma unroll
+      for (int dp = 0; dp < DP; ++dp) {
+        const float2 sv = *reinterpret_cast<const float2*>(cs + j * DFT + 2 * dp);
+        const u64_t st = pack2(sv.x, sv.y);
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) acc2[tt][dp] = ffma2(ww[tt], st, acc2[tt][dp]);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < DFT; ++d) {
+        const float st = cs[j * DFT + d];
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) acc[tt][d] = fmaf(w[tt + j], st, acc[tt][d]);
+      }
+    }
+  };
+
+  float w[2 * TT - 1];                              // Z[src0 + i0 + k], k = 0 .. 14
+  float nx[TT];                                     // the 8 values the NEXT step adds, loaded one step ahead
+  const int last = a.nlag + TT - 2;                 // last raw row (relative) any lag of this thread reads
+#pragma unroll
+  for (int k = 0; k < TT - 1; ++k) w[k] = zload(k);
+#pragma unroll
+  for (int k = 0; k < TT; ++k) nx[k] = zload(min(TT - 1 + k, last));
+  int i0 = 0;
+#pragma unroll 1
+  for (; i0 + TT <= a.nlag; i0 += TT) {
+#pragma unroll
+    for (int k = 0; k < TT; ++k) w[TT - 1 + k] = nx[k];
+#pragma unroll
+    for (int k = 0; k < TT; ++k) nx[k] = zload(min(i0 + 2 * TT - 1 + k, last));
+    const float* cs = c_st + i0 * DFT;
+#pragma unroll
+    for (int j = 0; j < TT; ++j) lag(w, cs, j);
+#pragma unroll
+    for (int k = 0; k < TT - 1; ++k) w[k] = w[k + TT];
+  }
+  const int rem = a.nlag - i0;                      // 0 .. 7 lags left
+  if (rem > 0) {
+#pragma unroll
+    for (int k = 0; k < TT - 1; ++k) w[TT - 1 + k] = nx[k];
+    const float* cs = c_st + i0 * DFT;
+#pragma unroll
+    for (int j = 0; j < TT - 1; ++j)
+      if (j < rem) lag(w, cs, j);
+  }
+  if (PACKED) {
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+      for (int dp = 0; dp < DP; ++dp) unpack2(acc2[tt][dp], acc[tt][2 * dp], acc[tt][2 * dp + 1]);
+  }
+}
 
 template <int DFT>
 __global__ void __launch_bounds__(128) temporal_project_const_kernel(const TemporalArgs a) {
@@ -152,45 +257,28 @@ __global__ void __launch_bounds__(128) temporal_project_const_kernel(const Tempo
   const long long k0 = grp * TT;
   const long long src0 = a.first_t + k0 - a.front;     // raw row feeding (row k0, lag 0)
 
-  auto zload = [&](long long src) -> float {
-    if (src < 0 || src >= a.n_raw_total) return 0.f;
-    const long long zr = src - a.z_src0;
-    return (zr >= 0 && zr < a.n_z) ? __ldg(a.Z + zr * a.ldz + q) : 0.f;
-  };
-
   float acc[TT][DFT];
 #pragma unroll
   for (int tt = 0; tt < TT; ++tt)
 #pragma unroll
     for (int d = 0; d < DFT; ++d) acc[tt][d] = 0.f;
-  float w[2 * TT - 1];                                  // Z[src0 + i0 + k], k = 0 .. 14
-#pragma unroll
-  for (int k = 0; k < TT - 1; ++k) w[k] = zload(src0 + k);
-  const int n_steps = (a.nlag + TT - 1) / TT;
-  for (int step = 0; step < n_steps; ++step) {
-    const int i0 = step * TT;
-#pragma unroll
-    for (int k = TT - 1; k < 2 * TT - 1; ++k) w[k] = zload(src0 + i0 + k);
-#pragma unroll
-    for (int j = 0; j < TT; ++j) {                      // lag i0 + j (zero basis rows past nlag)
-#pragma unroll
-      for (int d = 0; d < DFT; ++d) {
-        const float st = c_st[(i0 + j) * DFT + d];
-#pragma unroll
-        for (int tt = 0; tt < TT; ++tt) acc[tt][d] = fmaf(w[tt + j], st, acc[tt][d]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < TT - 1; ++k) w[k] = w[k + TT];
-  }
+  // raw rows [src0, src0 + nlag + TT - 1) feed this thread's 8 design rows
+  const long long n_win = a.nlag + TT - 1;
+  const long long zr0 = src0 - a.z_src0;
+  if (src0 >= 0 && src0 + n_win <= a.n_raw_total && zr0 >= 0 && zr0 + n_win <= a.n_z)
+    temporal_accumulate<DFT, true>(a, src0, q, acc);
+  else
+    temporal_accumulate<DFT, false>(a, src0, q, acc);
+
+  float* dst = a.out + (a.out_row0 + k0) * a.out_ld + a.col0 + q;
+  const bool full = k0 + TT <= a.n_out;
 #pragma unroll
   for (int tt = 0; tt < TT; ++tt) {
-    const long long k = k0 + tt;
-    if (k >= a.n_out) break;
-    float* dst = a.out + (a.out_row0 + k) * a.out_ld + a.col0 + q;
+    if (!full && k0 + tt >= a.n_out) break;
 #pragma unroll
     for (int d = 0; d < DFT; ++d)
       if (d < a.df_t) dst[(size_t)d * a.n_q] = acc[tt][d];
+    dst += a.out_ld;
   }
 }
 
