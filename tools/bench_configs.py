@@ -25,6 +25,13 @@ CONFIGS = {
     4: dict(name="config 4: LNLN 4 subunits softplus/softplus, elastic net 0.5/0.01, 2^24 samples, 80/20 train/dev",
             dims=[25, 20, 15], df=[8, 6, 6], n_raw=1 << 24, distr="poisson", out="softplus", filt="softplus",
             subunits=4, history=True, dev=0.2, alpha=0.5, beta=0.01, step=0.01, iters=40),
+    # not BASELINE configurations: the head counts between LNP (1) and config 4 (5)
+    6: dict(name="2 heads: 1 subunit with softplus filter nonlinearity + history, 2^23 samples",
+            dims=[25, 20, 15], df=[8, 6, 6], n_raw=1 << 23, distr="poisson", out="softplus", filt="softplus",
+            subunits=1, history=True, dev=0.0, alpha=1.0, beta=0.01, step=0.01, iters=40),
+    7: dict(name="3 heads: 2 subunits softplus/softplus + history, 2^23 samples",
+            dims=[25, 20, 15], df=[8, 6, 6], n_raw=1 << 23, distr="poisson", out="softplus", filt="softplus",
+            subunits=2, history=True, dev=0.0, alpha=1.0, beta=0.01, step=0.01, iters=40),
     5: dict(name="config 5: LG dims [40,32,32] df [12,10,10] (1200 coefficients), 2^24 samples",
             dims=[40, 32, 32], df=[12, 10, 10], n_raw=1 << 24, distr="gaussian", out="none", filt="none",
             subunits=1, history=False, dev=0.0, alpha=1.0, beta=0.001, step=0.01, iters=30),
