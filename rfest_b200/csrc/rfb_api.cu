@@ -285,7 +285,7 @@ static SweepFn sweep_instance(int Ht, int NCH, bool bwd, bool staged, int spec, 
   }
   INST(1, 1, 8) INST(1, 3, 8) INST(1, 5, 4) INST(1, 10, 2)
   INST(2, 1, 8) INST(2, 3, 8) INST(2, 5, 4) INST(2, 10, 1)
-  INST(3, 1, 8) INST(3, 3, 4) INST(3, 5, 2)
+  INST(3, 1, 8) INST(3, 3, 8) INST(3, 5, 4)
   INST(5, 1, 4) INST(5, 3, 4)
 #undef INST
   return nullptr;

@@ -591,13 +591,18 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
   for (int s = 0; s < NS; ++s)
     if (gw + (long long)s * GW < ntiles) issue(gw + (long long)s * GW, wbase + s * stage_bytes, bbase + 8u * s);
 
-  // multi-head layout: lane L <-> (head, row) = (L / RB, L % RB) among the first VP lanes
-  constexpr int V = H * RB;
+  // multi-head layout: lane L <-> (head, row) = (L / RBS, L % RBS) among the first VP lanes.  When
+  // H * RB exceeds the warp, the tile is handled as SUB sub-tiles of RBS rows: one stage, one barrier
+  // wait and one refill per tile, SUB independent epilogue chains that the scheduler interleaves.
+  constexpr int RBS = (H * RB <= 32) ? RB : RB / 2;
+  constexpr int SUB = RB / RBS;
+  constexpr int V = H * RBS;
   constexpr int VP = V <= 1 ? 1 : V <= 2 ? 2 : V <= 4 ? 4 : V <= 8 ? 8 : V <= 16 ? 16 : 32;
-  static_assert(V <= 32, "H * RB must not exceed the warp size");
+  static_assert(V <= 32, "H * RBS must not exceed the warp size");
+  static_assert(H > 1 || SUB == 1, "sub-tiles are a multi-head device");
   const int my_idx = lane & (VP - 1);
   const bool lane_valid = my_idx < V;
-  const int my_h = lane_valid ? my_idx / RB : 0;
+  const int my_h = lane_valid ? my_idx / RBS : 0;
   const float hic_lane = a.head_icpt[my_h];
   const int kind_lane = lane_valid ? a.head_nl[my_h] : RFB_NL_NONE;
   float sc_head = 0.f;
@@ -607,7 +612,7 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
 #pragma unroll
     for (int i = 0; i < NCH; ++i) use[h][i] = (H == 1) || ((a.head_slotmask[h] >> i) & 1u);
 
-  const int myr = (H == 1) ? (lane & (RB - 1)) : (my_idx % RB);
+  const int myr = (H == 1) ? (lane & (RB - 1)) : (my_idx % RBS);     // row inside the (sub-)tile
   int since_flush = 0;
   int buf = 0;
   uint32_t phase = 0;
@@ -616,48 +621,86 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
     const uint32_t bar = bbase + 8u * (uint32_t)buf;
     mbar_wait_a(bar, phase);
 
-    float4 x[RB][NCH];
+    // Three heads: weights + gradient accumulators take 72 registers, and holding 8 rows x 3 chunks of the
+    // tile from the forward to the backward pass on top of that does not fit.  REREAD: the rows are read
+    // from the shared-memory stage twice (once per pass, cheap) and the stage goes back to the copy engine
+    // after the backward pass -- which buys 8-row tiles (half as many per-tile epilogue chains per row;
+    // with 4-row tiles this shape ran at 60 % of the HBM rate while two heads with 8-row tiles saturate it).
+    constexpr bool REREAD = BWD && H == 3;   // (5 heads: measured slower with it, 6.9 vs 5.2 ms at config 4)
+    float4 x[REREAD ? 1 : RB][NCH];
+    if constexpr (!REREAD) {
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-      uint32_t ad = stage_addr + laddr[i];
+      for (int i = 0; i < NCH; ++i) {
+        uint32_t ad = stage_addr + laddr[i];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        x[r][i] = lds_f4(ad);
-        ad += lstride[i];
+        for (int r = 0; r < RB; ++r) {
+          x[r][i] = lds_f4(ad);
+          ad += lstride[i];
+        }
       }
     }
-    float yv = 0.f;
-    if (has_y) {
-      if (kStageY) yv = lds_f1(stage_addr + y_off + 4u * (uint32_t)myr);
-      else if (tile * RB + myr < a.n_rows) yv = __ldg(a.y + tile * RB + myr);
+    float yv[SUB];
+#pragma unroll
+    for (int sb = 0; sb < SUB; ++sb) {
+      yv[sb] = 0.f;
+      if (has_y) {
+        if (kStageY) yv[sb] = lds_f1(stage_addr + y_off + 4u * (uint32_t)(sb * RBS + myr));
+        else if (tile * RB + sb * RBS + myr < a.n_rows) yv[sb] = __ldg(a.y + tile * RB + sb * RBS + myr);
+      }
     }
 
     // forward: per (head, row) partial dot products (chunk slots a head has no columns in are
     // skipped warp-uniformly), then ONE transposed reduction over all H * RB values
-    float pv[VP];
+    float pv[SUB][VP];
+    if constexpr (!REREAD) {
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
+      for (int h = 0; h < H; ++h) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            if (use[h][i]) {
+              acc = fmaf(x[r][i].x, w[h][i].x, acc);
+              acc = fmaf(x[r][i].y, w[h][i].y, acc);
+              acc = fmaf(x[r][i].z, w[h][i].z, acc);
+              acc = fmaf(x[r][i].w, w[h][i].w, acc);
+            }
+          }
+          pv[r / RBS][h * RBS + (r % RBS)] = acc;
+        }
+      }
+    } else {
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          if (use[h][i]) {
-            acc = fmaf(x[r][i].x, w[h][i].x, acc);
-            acc = fmaf(x[r][i].y, w[h][i].y, acc);
-            acc = fmaf(x[r][i].z, w[h][i].z, acc);
-            acc = fmaf(x[r][i].w, w[h][i].w, acc);
+        for (int i = 0; i < NCH; ++i) x[0][i] = lds_f4(stage_addr + laddr[i] + (uint32_t)r * lstride[i]);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            if (use[h][i]) {
+              acc = fmaf(x[0][i].x, w[h][i].x, acc);
+              acc = fmaf(x[0][i].y, w[h][i].y, acc);
+              acc = fmaf(x[0][i].z, w[h][i].z, acc);
+              acc = fmaf(x[0][i].w, w[h][i].w, acc);
+            }
           }
+          pv[r / RBS][h * RBS + (r % RBS)] = acc;
         }
-        pv[h * RB + r] = acc;
       }
     }
+    float tot_lane[SUB];
 #pragma unroll
-    for (int k = V; k < VP; ++k) pv[k] = 0.f;
-    const float tot_lane = transpose_reduce<VP>(pv, lane);
+    for (int sb = 0; sb < SUB; ++sb) {
+#pragma unroll
+      for (int k = V; k < VP; ++k) pv[sb][k] = 0.f;
+      tot_lane[sb] = transpose_reduce<VP>(pv[sb], lane);
+    }
     // every lane's rows (and y) are in registers -- the dot products consumed them: hand the
     // buffer back to the copy engine for the tile NS ahead
-    {
+    if constexpr (!REREAD) {
       const long long nt = tile + (long long)NS * GW;
       __syncwarp();
       if (nt < ntiles) issue(nt, stage_addr, bar);
@@ -668,8 +711,8 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
     float r;
     if constexpr (H == 1) {
       const bool count = rowok && (lane < RB);
-      float tot[1] = {tot_lane}, dh[1];
-      row_epilogue<1, SPEC>(a, tot, hic, gic, poisson, rowok ? yv : 0.f, rowok, count, dh, r, sc);
+      float tot[1] = {tot_lane[0]}, dh[1];
+      row_epilogue<1, SPEC>(a, tot, hic, gic, poisson, rowok ? yv[0] : 0.f, rowok, count, dh, r, sc);
       if (a.r_out != nullptr && count) a.r_out[myrow] = r;
       if (BWD) {
 #pragma unroll
@@ -685,41 +728,56 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
         }
       }
     } else {
-      float delta_hr;
-      multihead_epilogue<H, RB, VP>(a, tot_lane, hic_lane, kind_lane, lane_valid, gic, poisson,
-                                    rowok ? yv : 0.f, rowok, lane, delta_hr, r, sc, sc_head);
-      if (a.r_out != nullptr && rowok && lane < RB) a.r_out[myrow] = r;
+      float delta_hr[SUB];
+#pragma unroll
+      for (int sb = 0; sb < SUB; ++sb) {
+        const long long srow = myrow + sb * RBS;
+        const bool sok = srow < a.n_rows;
+        multihead_epilogue<H, RBS, VP>(a, tot_lane[sb], hic_lane, kind_lane, lane_valid, gic, poisson,
+                                       sok ? yv[sb] : 0.f, sok, lane, delta_hr[sb], r, sc, sc_head);
+        if (a.r_out != nullptr && sok && lane < RBS) a.r_out[srow] = r;
+      }
       if (BWD) {
 #pragma unroll
         for (int rr = 0; rr < RB; ++rr) {
+          if constexpr (REREAD) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) x[0][i] = lds_f4(stage_addr + laddr[i] + (uint32_t)rr * lstride[i]);
+          }
+          const int xr = REREAD ? 0 : rr;
 #pragma unroll
           for (int h = 0; h < H; ++h) {
-            const float d = __shfl_sync(0xffffffffu, delta_hr, h * RB + rr);
+            const float d = __shfl_sync(0xffffffffu, delta_hr[rr / RBS], h * RBS + (rr % RBS));
 #pragma unroll
             for (int i = 0; i < NCH; ++i) {
               if (use[h][i]) {
-                g[h][i].x = fmaf(d, x[rr][i].x, g[h][i].x);
-                g[h][i].y = fmaf(d, x[rr][i].y, g[h][i].y);
-                g[h][i].z = fmaf(d, x[rr][i].z, g[h][i].z);
-                g[h][i].w = fmaf(d, x[rr][i].w, g[h][i].w);
+                g[h][i].x = fmaf(d, x[xr][i].x, g[h][i].x);
+                g[h][i].y = fmaf(d, x[xr][i].y, g[h][i].y);
+                g[h][i].z = fmaf(d, x[xr][i].z, g[h][i].z);
+                g[h][i].w = fmaf(d, x[xr][i].w, g[h][i].w);
               }
             }
           }
         }
       }
     }
+    if constexpr (REREAD) {       // both passes have read the stage: refill it for the tile NS ahead
+      const long long nt = tile + (long long)NS * GW;
+      __syncwarp();
+      if (nt < ntiles) issue(nt, stage_addr, bar);
+    }
     if (++buf == NS) {
       buf = 0;
       phase ^= 1u;
     }
     if (++since_flush >= a.flush_tiles) {
-      flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
-      if constexpr (H > 1) flush_head_scalar<H, RB>(my_acc, ctot, lane, sc_head);
+      flush_partials<H, NCH, RBS, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+      if constexpr (H > 1) flush_head_scalar<H, RBS>(my_acc, ctot, lane, sc_head);
       since_flush = 0;
     }
   }
-  flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
-  if constexpr (H > 1) flush_head_scalar<H, RB>(my_acc, ctot, lane, sc_head);
+  flush_partials<H, NCH, RBS, BWD>(my_acc, ctot, lane, cvalid, g, sc);
+  if constexpr (H > 1) flush_head_scalar<H, RBS>(my_acc, ctot, lane, sc_head);
   cta_reduce<H, NCH, BWD>(a, ctot, NE);
 }
 
