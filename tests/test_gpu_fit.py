@@ -638,10 +638,12 @@ def test_generic_sweep_wide_design_without_basis():
     assert w.shape == (1800, 1)
 
 
-def test_generic_sweep_many_subunits():
-    """7 subunits + history = 8 dot products per sample (more than the specialised kernels take)."""
+@pytest.mark.parametrize("out_nl", ["softplus", "softmax"])
+def test_generic_sweep_many_subunits(out_nl):
+    """7 subunits + history = 8 dot products per sample (more than the specialised kernels take); with a
+    softmax output the generic kernel's normaliser path runs as well."""
     stim, y, _ = helpers.lnp_data(1800, (8, 5, 4), seed=17)
-    g, o = _pair("poisson", "softplus")
+    g, o = _pair("poisson", out_nl)
     for m in (g, o):
         m.add_design_matrix(stim[:1400], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity="softplus",
                             name="stimulus")
