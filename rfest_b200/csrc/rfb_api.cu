@@ -1500,15 +1500,20 @@ static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float*
   slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, ds.n / 4096));
   a.n_slabs = slabs;
   const size_t n_entries = (size_t)ncols * ncols + 2 * (size_t)ncols;
-  double *d_part = nullptr, *d_out = nullptr;
-  CU(cudaMalloc(&d_part, sizeof(double) * n_entries * slabs));
-  CU(cudaMalloc(&d_out, sizeof(double) * n_entries));
-  a.part = d_part;
   static bool gram_attr = false;
   if (!gram_attr) {
     CU(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmem));
     gram_attr = true;
   }
+  double *d_part = nullptr, *d_out = nullptr;
+  if (cudaMalloc(&d_part, sizeof(double) * n_entries * slabs) != cudaSuccess ||
+      cudaMalloc(&d_out, sizeof(double) * n_entries) != cudaSuccess) {
+    cudaFree(d_part);
+    cudaGetLastError();
+    return fail(RFB_ERR_CUDA, "out of device memory for the Gram partial sums (%zu bytes)",
+                sizeof(double) * n_entries * (slabs + 1));
+  }
+  a.part = d_part;
   gram_kernel<<<dim3(a.n_pairs, slabs), kGramThreads, kGramSmem, e->stream>>>(a);
   gram_reduce_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, e->stream>>>(d_part, slabs, (long long)n_entries, d_out);
   e->launches += 2;
@@ -1582,7 +1587,10 @@ extern "C" int rfb_model_response_band(rfb_model* m, int kind, const float* b, c
   for (int f = 0; f < p.F; ++f) v_floats += (size_t)m->filters[f].n_coef * m->filters[f].n_coef;
   float *d_rows = nullptr, *d_small = nullptr, *d_out = nullptr;
   auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_small); cudaFree(d_out); };
-  CU(cudaMalloc(&d_rows, sizeof(float) * n * 2 * p.F));
+  if (cudaMalloc(&d_rows, sizeof(float) * std::max<size_t>(n, 1) * 2 * p.F) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(RFB_ERR_CUDA, "out of device memory");
+  }
   if (cudaMalloc(&d_small, sizeof(float) * (v_floats + p.P + 4)) != cudaSuccess) { cleanup(); return fail(RFB_ERR_CUDA, "out of device memory"); }
   if (!on_device && cudaMalloc(&d_out, sizeof(float) * n * 3) != cudaSuccess) { cleanup(); return fail(RFB_ERR_CUDA, "out of device memory"); }
   float* d_b = d_small + v_floats;
