@@ -78,15 +78,26 @@ def cpu_arm(log2n_workload, log2n_sample, steps, warmup):
           "history": (0.1 * np.random.default_rng(2047).standard_normal((8, 1))).astype(np.float32),
           "intercept": {"stimulus": 0.0, "history": 0.0, "global": 0.0}}
     m.y_pred["opt"] = {}
+    # all host cores for the BLAS calls, whatever OMP_NUM_THREADS says (torchrun sets it to 1 per rank)
+    cores = os.cpu_count()
+    blas_threads = None
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        limiter = threadpool_limits(limits=cores)
+        blas_threads = max([int(i.get("num_threads", 1)) for i in threadpool_info()] or [1])
+    except Exception:
+        limiter = None
     m.optimize(p0, warmup, "corrcoef", STEP_SIZE, 0, 0, "last")
     t0 = time.perf_counter()
     m.optimize(p0, steps, "corrcoef", STEP_SIZE, 0, 0, "last")
     dt = time.perf_counter() - t0
+    if limiter is not None:
+        limiter.restore_original_limits()
     its = steps / dt
     scaled = its * n / float(1 << log2n_workload)
-    cores = os.cpu_count()
     return {"value": scaled, "unit": "iterations/s", "cores": cores, "kind": "port",
-            "threads": torch.get_num_threads(),
+            "threads": blas_threads if blas_threads is not None else torch.get_num_threads(),
             "sample": f"oracle fp32 NumPy restatement, XS injected, n=2^{log2n_sample} rows x 296 cols, "
                       f"{steps} iterations in {dt:.2f} s = {its:.3f} it/s; linearly extrapolated to "
                       f"n=2^{log2n_workload}"}
@@ -320,7 +331,7 @@ def main():
         if rank != 0:
             return
         steps = max(args.steps, 1)
-        base = cpu_arm(args.log2n, args.cpu_log2n, min(steps, 10), min(max(args.warmup, 1), 3))
+        base = cpu_arm(args.log2n, args.cpu_log2n, min(steps, 60), min(max(args.warmup, 1), 5))
         out = {
             "impl": "reference",
             "metric": "spline-GLM fit iterations/s at the 2^%d x 288 design" % args.log2n,
