@@ -14,16 +14,16 @@ __all__ = ["eval_model_score", "compute_permutation_test", "significance", "resi
 
 
 def eval_model_score(model, X, y, stim=True, history=True, metric="corrcoef", w_type="opt"):
-    """check.py:9-21."""
-    if stim and history:
-        X_dict = {"stimulus": X, "history": y}
-    elif stim and not history:
-        X_dict = {"stimulus": X}
-    elif not stim and history:
-        X_dict = {"history": y}
-    else:
+    """check.py:9-21: score of the fitted model on (X, y); `stim` / `history` choose which of the two
+    filters take part (the history filter is driven by the response itself)."""
+    if not (stim or history):
         raise ValueError()
-    return model.score(X_test=X_dict, y_test=y, metric=metric, w_type=w_type)
+    inputs = {}
+    if stim:
+        inputs["stimulus"] = X
+    if history:
+        inputs["history"] = y
+    return model.score(X_test=inputs, y_test=y, metric=metric, w_type=w_type)
 
 
 def compute_permutation_test(model, X_test, y_test, n_perm=100, history=True, metric="corrcoef",
@@ -54,19 +54,17 @@ def compute_permutation_test(model, X_test, y_test, n_perm=100, history=True, me
 
 
 def significance(model, w_type="opt", show_results=False):
-    """check.py:103-126: Wald test of every filter's coefficients against zero."""
+    """check.py:103-126: Wald test of every filter's coefficients against zero,
+    W = p^T V^-1 p ~ chi2(sum(df))."""
     W_values, p_values = {}, {}
     for name in model.filter_names:
-        p = np.asarray(model.p[w_type][name], dtype=np.float64)
-        W = np.squeeze(p.T @ np.linalg.inv(np.asarray(model.V[w_type][name], dtype=np.float64)) @ p)
-        p_value = 1 - scipy.stats.chi2.cdf(x=W, df=sum(model.df[name]))
-        W_values[name] = W
-        p_values[name] = p_value
+        coef = np.asarray(model.p[w_type][name], dtype=np.float64)
+        cov = np.asarray(model.V[w_type][name], dtype=np.float64)
+        W_values[name] = np.squeeze(coef.T @ np.linalg.solve(cov, coef))
+        p_values[name] = scipy.stats.chi2.sf(W_values[name], df=sum(model.df[name]))
         if show_results:
-            if p_value < 0.05:
-                print(f"{name}: \n\tsignificant \n\tW={W:.3f}, p_value={p_value:.3f}")
-            else:
-                print(f"{name}: \n\tnot significant \n\tW={W:.3f}, p_value={p_value:.3f}")
+            verdict = "significant" if p_values[name] < 0.05 else "not significant"
+            print(f"{name}: \n\t{verdict} \n\tW={W_values[name]:.3f}, p_value={p_values[name]:.3f}")
     return W_values, p_values
 
 
