@@ -50,6 +50,11 @@ struct SweepArgs {
   int flush_tiles;                  // fp32 -> fp64 flush cadence, in tiles
   int n_stages;                     // staged variant: depth of each warp's copy ring
   const float* softmax;             // out_nl == RFB_NL_SOFTMAX: {1 / Z, D} on the device (see softmax_scale)
+  // subunit sweep (sweep_sub.cuh): K heads share the block of slot `sub_slot`; at most one other head
+  int sub_slot;
+  int sub_head[4];                  // head index (accumulator layout) of every subunit
+  int sub_extra_head;               // head over the remaining (<= 8) chunks, -1: none
+  int layout_heads;                 // heads in the accumulator layout (the plan's template head count)
 };
 
 // One-shot exchange over NVLink peer memory (multi-GPU): every rank owns a buffer
@@ -68,6 +73,23 @@ struct XchgArgs {
   unsigned long long* seq;             // local device counter: completed exchanges
   unsigned int* done;                  // local device counter for "last CTA" detection
 };
+
+// Packed fp32 arithmetic: two IEEE fused multiply-adds on a 64-bit register pair for one issue slot
+// (fma.rn.f32x2, SASS FFMA2; bit-identical to the scalar ones).
+typedef unsigned long long u64_t;
+__device__ __forceinline__ u64_t pack2(float lo, float hi) {
+  u64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64_t ffma2(u64_t a, u64_t b, u64_t c) {
+  u64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 
 __host__ __device__ inline int sweep_num_entries(int H, int n_chunks) {
   return H * n_chunks * 4 + kNumScalars;

@@ -149,21 +149,6 @@ __constant__ float c_st[kTempMaxLag * 16];
 // pair and are updated by one fma.rn.f32x2 (SASS FFMA2) -- two IEEE fused multiply-adds, bit-identical to the
 // scalar ones, for one issue slot.  The kernel was issue-bound (65 % of its instructions were FFMAs at 75 %
 // issue utilisation); halving the FMA instructions puts it on the FMA pipe itself.
-typedef unsigned long long u64_t;
-__device__ __forceinline__ u64_t pack2(float lo, float hi) {
-  u64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(u64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64_t ffma2(u64_t a, u64_t b, u64_t c) {
-  u64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 template <int DFT, bool FAST>
 __device__ __forceinline__ void temporal_accumulate(const TemporalArgs& a, long long src0, int q, float (&acc)[8][DFT]) {
   constexpr int TT = 8;

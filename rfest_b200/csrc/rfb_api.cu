@@ -19,6 +19,7 @@
 #include "project.cuh"
 #include "project_tc.cuh"
 #include "sweep.cuh"
+#include "sweep_sub.cuh"
 #include "softmax.cuh"
 #include "update.cuh"
 
@@ -125,6 +126,7 @@ struct rfb_engine {
   int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
   int sweep_stages = 0;   // depth of each warp's copy ring (0: sized for ~112 KB in flight per SM)
   int sweep_warps = 4;    // warps per CTA
+  int sweep_sub = 1;      // subunit models (several heads on one block) on the subunit sweep (sweep_sub.cuh)
   int sweep_ctas = -1;    // CTAs per SM (0: as many as fit; -1: auto = 1 for single-head models, where
                           // 4 warps x 3 stages measured best, as many as fit for the compute-heavier multi-head ones)
 };
@@ -182,6 +184,15 @@ struct SweepBuffers {
   int threads = 0;
   int staged = 0, stages = 0;
   size_t smem = 0;
+  bool sub = false;   // this data set runs the subunit sweep
+};
+
+// subunit pattern: K heads whose columns are ONE shared block, at most one other head on <= 8 chunks
+struct SubPlan {
+  bool ok = false;
+  int slot = 0, K = 0, NJ = 0, c0 = 0;
+  int heads[kSubMaxK] = {};
+  int extra_head = -1;
 };
 
 struct Plan {
@@ -200,6 +211,7 @@ struct Plan {
   std::vector<unsigned> head_slotmask;  // [Ht] chunk slots (of 32 chunks) each head has columns in
   std::vector<int> entry_of;   // [P]
   std::vector<int> coef0;      // [F] offset of the filter's coefficients in b
+  SubPlan sub;
 };
 
 struct ParamSet {  // device-side parameter image + what the sweep reads
@@ -273,6 +285,21 @@ static SweepFn pick_variant(bool bwd, bool staged, int spec) {
   return pick_staged<H, NCH, RB, 0>(bwd);
 }
 
+template <int K, int NJ>
+static SweepFn pick_sub(bool bwd, int spec) {
+  if (spec == 1)
+    return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, true, 1> : (SweepFn)sweep_subunit_kernel<K, NJ, false, 1>;
+  return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, true, 0> : (SweepFn)sweep_subunit_kernel<K, NJ, false, 0>;
+}
+static int sub_template_nj(int nj) { return nj <= 3 ? 3 : kSubMaxNJ; }
+static SweepFn sub_instance(int K, int NJ, bool bwd, int spec) {
+#define INST(k, nj) \
+  if (K == k && NJ == nj) return pick_sub<k, nj>(bwd, spec);
+  INST(2, 3) INST(3, 3) INST(4, 3) INST(2, 9) INST(3, 9) INST(4, 9)
+#undef INST
+  return nullptr;
+}
+
 static int template_heads(int H) { return H <= 1 ? 1 : H <= 2 ? 2 : H <= 3 ? 3 : 5; }
 static int template_chunks(int nch) { return nch <= 1 ? 1 : nch <= 3 ? 3 : nch <= 5 ? 5 : 10; }
 
@@ -342,6 +369,29 @@ static int build_plan(rfb_model* m) {
   p.head_nl.assign(p.Ht, RFB_NL_NONE);
   for (int h = 0; h < p.H; ++h) p.head_nl[h] = heads[h].nl;
   p.NE = sweep_num_entries(p.Ht, p.n_chunks);
+  if (!p.generic && p.H >= 2) {
+    for (int s = 0; s < n_slots && !p.sub.ok; ++s) {
+      SubPlan sp;
+      int others = 0;
+      bool clean = true;
+      for (int h = 0; h < p.H; ++h) {
+        if (heads[h].slots == (1u << s)) {
+          if (sp.K < kSubMaxK) sp.heads[sp.K] = h;
+          ++sp.K;
+        } else {
+          if (heads[h].slots & (1u << s)) clean = false;   // a merged head also reads the shared block
+          sp.extra_head = h;
+          ++others;
+        }
+      }
+      sp.slot = s;
+      sp.c0 = p.slot_chunk0[s + 1] - p.slot_chunk0[s];
+      sp.NJ = sub_template_nj((sp.c0 + 7) / 8);
+      sp.ok = clean && sp.K >= 2 && sp.K <= kSubMaxK && others <= 1 && sp.c0 <= 8 * kSubMaxNJ &&
+              p.n_chunks - sp.c0 <= 8 && (others == 1 || p.n_chunks == sp.c0);
+      if (sp.ok) p.sub = sp;
+    }
+  }
 
   p.coef0.resize(p.F);
   p.P = 0;
@@ -477,6 +527,56 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
     sb.smem = 0;
     return RFB_OK;
   }
+  bool all_slots = true;
+  for (int s = 0; s < p.n_slots; ++s) all_slots = all_slots && s < ds.n_slots && ds.blocks[s] != nullptr;
+  if (p.sub.ok && e->sweep_sub && e->sweep_staged && all_slots) {
+    // subunit sweep (sweep_sub.cuh): 8-row tiles, rows stay in the stage through both passes
+    const SubPlan& sp = p.sub;
+    int st = e->sweep_stages > 0 ? e->sweep_stages : 2;
+    int occ = 0;
+    size_t smem = 0;
+    bool fits = false;
+    for (; st >= 2 && !fits; --st) {
+      smem = sweep_sub_smem_bytes(warps, st, p.ctot, sp.K, sp.NJ, sp.c0);
+      fits = true;
+      occ = 1 << 30;
+      for (int bwd = 0; bwd < 2 && fits; ++bwd) {
+        for (int spec = 0; spec < 2 && fits; ++spec) {
+          SweepFn fn = sub_instance(sp.K, sp.NJ, bwd != 0, spec);
+          if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no subunit sweep instance");
+          if (smem > 48 * 1024 &&
+              cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            fits = false;
+            break;
+          }
+          int o = 0;
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, threads, smem));
+          occ = std::min(occ, o);
+        }
+      }
+      if (fits && occ < 1) fits = false;
+      if (fits) break;
+    }
+    if (fits) {
+      if (e->sweep_ctas > 0) occ = std::min(occ, e->sweep_ctas);
+      const int64_t ntiles = (ds.n + kSubRows - 1) / kSubRows;
+      int64_t grid = (int64_t)e->num_sms * occ;
+      const int64_t need = (ntiles + warps - 1) / warps;
+      if (grid > need) grid = std::max<int64_t>(need, 1);
+      sb.warp_acc_bytes = sizeof(double) * (size_t)grid * warps * p.NE;
+      sb.cta_part_bytes = sizeof(double) * (size_t)grid * p.NE;
+      CU(cudaMalloc(&sb.warp_acc, sb.warp_acc_bytes));
+      CU(cudaMalloc(&sb.cta_part, sb.cta_part_bytes));
+      sb.grid = (int)grid;
+      sb.threads = threads;
+      sb.staged = 1;
+      sb.stages = st;
+      sb.smem = smem;
+      sb.sub = true;
+      return RFB_OK;
+    }
+  }
   int staged = e->sweep_staged ? 1 : 0;
   int stages = e->sweep_stages;
   if (stages <= 0) {
@@ -544,7 +644,14 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   TRY(ensure_sweep_buffers(m, kind));
   SweepBuffers& sb = m->sb[kind];
   SweepFn fn = nullptr;
-  if (!p.generic) {
+  const int eff_out_nl = out_nl_override >= 0 ? out_nl_override : m->out_nl;
+  if (sb.sub) {
+    int spec = (m->distr == RFB_DISTR_POISSON && eff_out_nl == RFB_NL_SOFTPLUS) ? 1 : 0;
+    for (int k = 0; k < p.sub.K; ++k)
+      if (head_nl[p.sub.heads[k]] != RFB_NL_SOFTPLUS) spec = 0;
+    fn = sub_instance(p.sub.K, p.sub.NJ, bwd, spec);
+    if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no subunit sweep instance");
+  } else if (!p.generic) {
     fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, sweep_spec(m, head_nl), &RB);
     if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
   }
@@ -576,7 +683,13 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   a.r_out = r_out;
   a.flush_tiles = std::max(1, 256 / RB);
   a.n_stages = sb.stages;
-  if (p.generic) {
+  a.layout_heads = p.Ht;
+  a.sub_slot = p.sub.slot;
+  for (int k = 0; k < kSubMaxK; ++k) a.sub_head[k] = p.sub.heads[k];
+  a.sub_extra_head = p.sub.extra_head;
+  if (sb.sub) {
+    fn<<<sb.grid, sb.threads, sb.smem, e->stream>>>(a);
+  } else if (p.generic) {
     if (bwd) sweep_generic_kernel<true><<<sb.grid, sb.threads, 0, e->stream>>>(a, p.Ht);
     else sweep_generic_kernel<false><<<sb.grid, sb.threads, 0, e->stream>>>(a, p.Ht);
   } else {
@@ -672,6 +785,7 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   if (const char* v = getenv("RFB_SWEEP_STAGES")) e->sweep_stages = atoi(v);
   if (const char* v = getenv("RFB_SWEEP_WARPS")) e->sweep_warps = atoi(v);
   if (const char* v = getenv("RFB_SWEEP_CTAS")) e->sweep_ctas = atoi(v);
+  if (const char* v = getenv("RFB_SWEEP_SUB")) e->sweep_sub = atoi(v);
   if (const char* v = getenv("RFB_PROJECT_TC")) e->project_tc = atoi(v);
   if (const char* v = getenv("RFB_XCHG")) e->use_xchg = atoi(v);
   *out = e;
@@ -685,6 +799,7 @@ extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) 
   else if (k == "sweep_stages") e->sweep_stages = value;
   else if (k == "sweep_warps") e->sweep_warps = value;
   else if (k == "sweep_ctas") e->sweep_ctas = value;
+  else if (k == "sweep_sub") e->sweep_sub = value;
   else if (k == "project_tc") e->project_tc = value;
   else if (k == "xchg") e->use_xchg = value;
   else return fail(RFB_ERR_INVALID, "unknown option '%s'", key);

@@ -1,0 +1,421 @@
+// K2s: the streaming sweep for subunit models (LNLN: `num_subunits` filters that alias ONE projected
+// design block, rfest/GLM/_glm.py:338-352, each with its own filter nonlinearity, plus at most one
+// other head such as the history filter).
+//
+// The row-per-warp kernels of sweep.cuh keep every head's weights in registers and reduce each
+// (head, row) dot product over all 32 lanes: with 4 subunits + history that is 250 warp instructions
+// per row (62 forward + 62 backward FFMA, 31 for the transposed reductions, 30 for one epilogue chain per
+// 4 rows ...) against a budget of ~200 issue slots per row at HBM speed -- instruction-bound at half the
+// HBM rate (profiles/README.md).  This kernel changes the mapping instead of the arithmetic:
+//   * a row is owned by 8 lanes (lane l8 holds the float4 chunks l8, l8 + 8, ...), a warp works on
+//     4 rows at a time and a tile is 2 such passes (8 rows): a (head, row) dot product is reduced over 8
+//     lanes, the 4 heads x 2 passes of a lane's rows by ONE transposed butterfly of 7 shuffles;
+//   * the head weights live in shared memory (one 128-byte broadcast LDS per head and chunk serves all
+//     4 row groups and both passes) -- registers hold only the gradient accumulators, so no columns
+//     are padded to the warp width (288 columns = 9 chunks per lane exactly);
+//   * products are packed (fma.rn.f32x2): the 8-byte halves of a chunk against the same halves of the
+//     weights forward, (delta, delta) against the chunk backward;
+//   * the rows are read from the shared-memory stage twice (forward, backward) instead of being held;
+//   * the epilogue runs once per tile with lane = (row group, pass, head): all 32 lanes evaluate one
+//     filter nonlinearity each.
+// About 75 warp instructions per row for 4 subunits + history.  Same staging (per-warp ring of bulk-async
+// copies), same accumulator layout, same fixed-order fp64 reductions as sweep.cuh: bit-reproducible.
+#pragma once
+
+#include "sweep.cuh"
+
+namespace rfb {
+
+constexpr int kSubRows = 8;      // rows per tile: 2 passes x 4 row groups
+constexpr int kSubMaxK = 4;      // subunit heads
+constexpr int kSubMaxNJ = 9;     // chunks per lane: up to 72 chunks = 288 columns in the shared block
+constexpr int kSubFlushTiles = 64;
+
+// Shared memory.  A stage = the 8-row tile of every design block, 32 B of responses and a zero pad: lane l8
+// reads the chunks l8 + 8 j, j < NJ, of its rows with compile-time offsets; the chunk slots past the block's
+// C0 chunks have zero weights and read on into the next row / block / responses / pad -- finite data that
+// the pad keeps inside the stage.  Then the mbarriers, then the weights [K][8 NJ] float4 (zero past C0).
+__host__ __device__ inline size_t sweep_sub_stage_bytes(int ctot, int NJ, int c0) {
+  return (size_t)kSubRows * ctot * sizeof(float) + 32 + (size_t)(8 * NJ - c0) * 16;
+}
+__host__ __device__ inline size_t sweep_sub_w_offset(int warps, int stages, int ctot, int NJ, int c0) {
+  return ((size_t)warps * stages * (sweep_sub_stage_bytes(ctot, NJ, c0) + 8) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t sweep_sub_smem_bytes(int warps, int stages, int ctot, int K, int NJ, int c0) {
+  return sweep_sub_w_offset(warps, stages, ctot, NJ, c0) + (size_t)K * 8 * NJ * 16;
+}
+
+__device__ __forceinline__ void lds_2x64(uint32_t addr, u64_t& lo, u64_t& hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
+
+// p[i] = this lane's partial of value i; afterwards every lane of an 8-lane group holds the group's
+// sum of value (lane & (VN - 1)).
+template <int VN>
+__device__ __forceinline__ float transpose_reduce8(float (&p)[VN], int lane) {
+#pragma unroll
+  for (int s = VN / 2; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float keep = up ? p[j + s] : p[j];
+      const float send = up ? p[j] : p[j + s];
+      p[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  float v = p[0];
+#pragma unroll
+  for (int m = VN; m < 8; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// SPEC 0: run-time nonlinearities / distribution; 1: softplus subunits, softplus output, Poisson
+template <int K, int NJ, bool BWD, int SPEC>
+__global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const __grid_constant__ SweepArgs a) {
+  static_assert(K >= 2 && K <= kSubMaxK && NJ >= 1 && NJ <= kSubMaxNJ, "shape");
+  constexpr int RT = kSubRows;
+  constexpr int KP = K <= 2 ? 2 : 4;   // heads padded to a power of two
+  constexpr int VN = 2 * KP;           // (head, pass) values per row group
+  extern __shared__ __align__(128) unsigned char sweep_smem[];
+  const int lane = threadIdx.x & 31, l8 = lane & 7, rg = lane >> 3;
+  const int wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const long long gw = (long long)blockIdx.x * wpc + wic;
+  const long long GW = (long long)gridDim.x * wpc;
+  const int ctot = a.n_chunks * 4;
+  const int NE = a.layout_heads * ctot + kNumScalars;
+  const int NS = a.n_stages;
+  const int S = a.sub_slot, cs0 = a.slot_chunk0[S], C0 = a.slot_chunk0[S + 1] - cs0;
+  const uint32_t stage_bytes = (uint32_t)sweep_sub_stage_bytes(ctot, NJ, C0);
+  const uint32_t y_off = (uint32_t)(RT * ctot * sizeof(float));
+  const uint32_t ldS = (uint32_t)(a.slot_ld[S] * sizeof(float));
+
+  const uint32_t sbase = smem_u32(sweep_smem);
+  const uint32_t wbase = sbase + (uint32_t)wic * NS * stage_bytes;
+  const uint32_t bbase = sbase + (uint32_t)wpc * NS * stage_bytes + (uint32_t)wic * NS * 8u;
+  const uint32_t wsm = sbase + (uint32_t)sweep_sub_w_offset(wpc, NS, ctot, NJ, C0);
+  constexpr uint32_t wstride = 8u * NJ * 16u;
+  const uint32_t wl8 = wsm + (uint32_t)l8 * 16u;
+
+  // ---- head weights -> shared memory -----------------------------------------------------------------
+  for (int idx = threadIdx.x; idx < K * 8 * NJ; idx += blockDim.x) {
+    const int k = idx / (8 * NJ), c = idx - k * (8 * NJ);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C0) v = *reinterpret_cast<const float4*>(a.W + (size_t)a.sub_head[k] * ctot + 4 * (cs0 + c));
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wsm + (uint32_t)idx * 16u), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+
+  // the other head: lane l8 owns chunk l8 of the remaining columns (at most 8 chunks)
+  const int E = a.n_chunks - C0;
+  const int he = a.sub_extra_head;
+  uint32_t eoff = (uint32_t)(RT * 16 * cs0), estride = ldS;
+  float4 we = make_float4(0.f, 0.f, 0.f, 0.f), ge = make_float4(0.f, 0.f, 0.f, 0.f);
+  int ecol = -1;
+  if (l8 < E && he >= 0) {
+    const int c = l8 < cs0 ? l8 : l8 + C0;
+    int s = 0;
+    while (s + 1 < a.n_slots && c >= a.slot_chunk0[s + 1]) ++s;
+    eoff = (uint32_t)(RT * 16 * a.slot_chunk0[s] + 16 * (c - a.slot_chunk0[s]));
+    estride = (uint32_t)(a.slot_ld[s] * sizeof(float));
+    we = *reinterpret_cast<const float4*>(a.W + (size_t)he * ctot + 4 * c);
+    ecol = 4 * c;
+  }
+
+  // ---- this lane's place in the epilogue: (row group, pass, head) -----------------------------------
+  const int my_idx = l8 & (VN - 1);
+  const int my_k = my_idx % KP, my_p = my_idx / KP;
+  const bool head_ok = my_k < K;
+  const bool lane_counts = l8 < VN;                 // K <= 2: lanes 4..7 of a group are duplicates
+  const int my_head = head_ok ? a.sub_head[my_k] : 0;
+  const float hic_lane = head_ok ? a.head_icpt[my_head] : 0.f;
+  const int kind_lane = head_ok ? a.head_nl[my_head] : RFB_NL_NONE;
+  const int kind_e = he >= 0 ? a.head_nl[he] : kNlAbsent;
+  const float hic_e = he >= 0 ? a.head_icpt[he] : 0.f;
+  const float gic = a.glob_icpt[0];
+  const bool poisson = SPEC == 1 ? true : (a.distr == RFB_DISTR_POISSON);
+  const int out_kind = SPEC == 1 ? RFB_NL_SOFTPLUS : a.out_nl;
+
+  u64_t glo[K][NJ], ghi[K][NJ];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) glo[k][j] = ghi[k][j] = 0ull;
+  float sc[S_GHEAD];
+#pragma unroll
+  for (int k = 0; k < S_GHEAD; ++k) sc[k] = 0.f;
+  float sc_head = 0.f, sc_e = 0.f;
+  double* my_acc = a.warp_acc + (size_t)gw * NE;
+  for (int e = lane; e < NE; e += 32) my_acc[e] = 0.0;
+
+  // ---- the copies: lane s moves design block s, lane n_slots moves the responses --------------------
+  const char* my_src = nullptr;
+  uint32_t my_rowbytes = 0, my_dst = 0, all_rowbytes = 0;
+  for (int s = 0; s < a.n_slots; ++s) {
+    all_rowbytes += (uint32_t)(a.slot_ld[s] * sizeof(float));
+    if (lane == s) {
+      my_src = reinterpret_cast<const char*>(a.slot_ptr[s]);
+      my_rowbytes = (uint32_t)(a.slot_ld[s] * sizeof(float));
+      my_dst = (uint32_t)(RT * 4 * a.slot_chunk0[s] * sizeof(float));
+    }
+  }
+  const bool has_y = a.y != nullptr;
+  const bool y_lane = has_y && lane == a.n_slots;
+  if (y_lane) {
+    my_src = reinterpret_cast<const char*>(a.y);
+    my_rowbytes = sizeof(float);
+    my_dst = y_off;
+  }
+  const uint32_t tile_y_bytes = has_y ? 32u : 0u;
+  const uint64_t policy = l2_evict_first_policy();
+  const long long ntiles = (a.n_rows + RT - 1) / RT;
+
+  auto issue = [&](long long tile, uint32_t stage_addr, uint32_t bar) {
+    const long long row0 = tile * RT;
+    const long long left = a.n_rows - row0;
+    const uint32_t rows = left < RT ? (uint32_t)left : (uint32_t)RT;
+    if (lane == 0) mbar_arrive_expect_tx_a(bar, rows * all_rowbytes + tile_y_bytes);
+    if (my_rowbytes != 0) {
+      const uint32_t bytes = y_lane ? 32u : rows * my_rowbytes;
+      bulk_g2s_a(stage_addr + my_dst, my_src + row0 * my_rowbytes, bytes, bar, policy);
+    }
+  };
+
+  for (uint32_t o = lane * 4u; o < (uint32_t)NS * stage_bytes; o += 128u)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(wbase + o), "r"(0u) : "memory");
+  if (lane == 0)
+    for (int s = 0; s < NS; ++s) mbar_init_a(bbase + 8u * s, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();                                   // weights visible to every warp
+  for (int s = 0; s < NS; ++s)
+    if (gw + (long long)s * GW < ntiles) issue(gw + (long long)s * GW, wbase + s * stage_bytes, bbase + 8u * s);
+
+  auto flush = [&]() {
+    if (BWD) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          float v[4];
+          unpack2(glo[k][j], v[0], v[1]);
+          unpack2(ghi[k][j], v[2], v[3]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {               // the 4 row groups hold partial sums of the same columns
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+          }
+          if (rg == (j & 3) && l8 + 8 * j < C0) {
+            double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)a.sub_head[k] * ctot + 4 * (cs0 + l8 + 8 * j));
+            double2 lo = p2[0], hi = p2[1];
+            lo.x += (double)v[0]; lo.y += (double)v[1];
+            hi.x += (double)v[2]; hi.y += (double)v[3];
+            p2[0] = lo;
+            p2[1] = hi;
+          }
+          glo[k][j] = ghi[k][j] = 0ull;
+        }
+      }
+      float v[4] = {ge.x, ge.y, ge.z, ge.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+        v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+      }
+      if (rg == 0 && ecol >= 0) {
+        double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)he * ctot + ecol);
+        double2 lo = p2[0], hi = p2[1];
+        lo.x += (double)v[0]; lo.y += (double)v[1];
+        hi.x += (double)v[2]; hi.y += (double)v[3];
+        p2[0] = lo;
+        p2[1] = hi;
+      }
+      ge = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double* scal = my_acc + (size_t)a.layout_heads * ctot;
+#pragma unroll
+    for (int k = 0; k < S_GHEAD; ++k) {
+      const double v = warp_sum_f64((double)sc[k]);
+      if (lane == 0) scal[k] += v;
+      sc[k] = 0.f;
+    }
+    {
+      double v = (double)sc_head;                      // lanes with the same head: l8 bits >= KP, row groups
+#pragma unroll
+      for (int m = KP; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (lane < K) scal[S_GHEAD + a.sub_head[lane]] += v;
+      sc_head = 0.f;
+      const double ve = warp_sum_f64((double)sc_e);
+      if (lane == 0 && he >= 0) scal[S_GHEAD + he] += ve;
+      sc_e = 0.f;
+    }
+  };
+
+  const uint32_t xlane = (uint32_t)(RT * 16 * cs0) + (uint32_t)rg * ldS + (uint32_t)l8 * 16u;
+  int since_flush = 0;
+  int buf = 0;
+  uint32_t phase = 0;
+  for (long long tile = gw; tile < ntiles; tile += GW) {
+    const uint32_t stage_addr = wbase + (uint32_t)buf * stage_bytes;
+    const uint32_t bar = bbase + 8u * (uint32_t)buf;
+    mbar_wait_a(bar, phase);
+    const uint32_t xa0 = stage_addr + xlane;          // pass 0: row rg, chunk l8
+    const uint32_t xa1 = xa0 + 4u * ldS;              // pass 1: row 4 + rg
+
+    // ---- forward: per (head, pass) packed partial dot products over this lane's chunks ----------------
+    u64_t acc[K][2];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k][0] = acc[k][1] = 0ull;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      u64_t x0l, x0h, x1l, x1h;
+      lds_2x64(xa0 + 128u * j, x0l, x0h);
+      lds_2x64(xa1 + 128u * j, x1l, x1h);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        u64_t wl, wh;
+        lds_2x64(wl8 + (uint32_t)k * wstride + 128u * j, wl, wh);
+        acc[k][0] = ffma2(x0l, wl, acc[k][0]);
+        acc[k][1] = ffma2(x1l, wl, acc[k][1]);
+        acc[k][0] = ffma2(x0h, wh, acc[k][0]);
+        acc[k][1] = ffma2(x1h, wh, acc[k][1]);
+      }
+    }
+    const float4 xe0 = lds_f4(stage_addr + eoff + (uint32_t)rg * estride);
+    const float4 xe1 = lds_f4(stage_addr + eoff + (uint32_t)(4 + rg) * estride);
+    float ae0 = fmaf(xe0.x, we.x, fmaf(xe0.y, we.y, fmaf(xe0.z, we.z, xe0.w * we.w)));
+    float ae1 = fmaf(xe1.x, we.x, fmaf(xe1.y, we.y, fmaf(xe1.z, we.z, xe1.w * we.w)));
+    float yv = 0.f;
+    if (has_y) yv = lds_f1(stage_addr + y_off + 4u * (uint32_t)(my_p * 4 + rg));
+
+    float pv[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) pv[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        float lo, hi;
+        unpack2(acc[k][p], lo, hi);
+        pv[k + KP * p] = lo + hi;
+      }
+    }
+    const float tot = transpose_reduce8<VN>(pv, lane);
+    float aet;
+    {
+      const bool up = (l8 & KP) != 0;                  // == my_p
+      aet = (up ? ae1 : ae0) + __shfl_xor_sync(0xffffffffu, up ? ae0 : ae1, KP);
+#pragma unroll
+      for (int m = 1; m < 8; m <<= 1)
+        if (m != KP) aet += __shfl_xor_sync(0xffffffffu, aet, m);
+    }
+
+    // ---- epilogue, lane = (row group, pass, head) -------------------------------------------------------
+    const long long myrow = tile * RT + my_p * 4 + rg;
+    const bool rowok = myrow < a.n_rows;
+    if (!rowok) yv = 0.f;
+    float f, dphi;
+    nl_eval(SPEC == 1 ? RFB_NL_SOFTPLUS : kind_lane, tot + hic_lane, f, dphi);
+    float u = head_ok ? f : 0.f;
+#pragma unroll
+    for (int m = 1; m < KP; m <<= 1) u += __shfl_xor_sync(0xffffffffu, u, m);
+    float fe, dpe;
+    nl_eval(kind_e, aet + hic_e, fe, dpe);             // warp-uniform kind
+    u += fe;
+    u += gic;
+    float r, dr;
+    nl_eval(out_kind, u, r, dr);
+    if (SPEC == 0) softmax_scale(a, out_kind, r);
+    float la, lb, dldr;
+    const float err = yv - r;
+    if (poisson) {                                     // rfest/loss.py:4-11
+      const bool fin = r != CUDART_INF_F;
+      const float r1 = fin ? r : 0.f;
+      const bool live = fin && (r1 > 1e-20f);
+      const float r2 = (r1 != r1) ? r1 : fmaxf(r1, 1e-20f);
+      la = -logf(r2) * yv;
+      lb = r2;
+      dldr = live ? (1.0f - fast_div(yv, r2)) : 0.f;
+    } else {                                           // rfest/loss.py:14-16
+      la = err * err;
+      lb = 0.f;
+      dldr = -err * a.two_over_n;
+    }
+    float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
+    if (SPEC == 0) delta = softmax_delta(a, out_kind, delta, r, dldr, rowok);
+    const bool sm_out = SPEC == 0 && out_kind == RFB_NL_SOFTMAX;
+    const bool count_row = rowok && lane_counts && my_k == 0;
+    if (count_row) {
+      sc[S_LOSS_A] += la;
+      sc[S_LOSS_B] += lb;
+      sc[S_R] += r;
+      sc[S_RR] += r * r;
+      sc[S_YR] += yv * r;
+      sc[S_SQERR] += err * err;
+      if (!sm_out) sc[S_GGLOBAL] += delta;
+      if (a.r_out != nullptr) a.r_out[myrow] = r;
+    }
+    const float delta_k = (delta == 0.f || !head_ok) ? 0.f : delta * dphi;
+    const float delta_e = (delta == 0.f) ? 0.f : delta * dpe;
+    if (lane_counts && !(sm_out && kind_lane == RFB_NL_NONE)) sc_head += delta_k;
+    if (count_row && !(sm_out && kind_e == RFB_NL_NONE)) sc_e += delta_e;
+
+    // ---- backward: G_k += delta_k x, rows read from the stage a second time -----------------------------
+    if (BWD) {
+      u64_t dd[K][2];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const float d = __shfl_sync(0xffffffffu, delta_k, (lane & 24) | (k + KP * p));
+          dd[k][p] = pack2(d, d);
+        }
+      }
+      const float de0 = __shfl_sync(0xffffffffu, delta_e, lane & 24);
+      const float de1 = __shfl_sync(0xffffffffu, delta_e, (lane & 24) | KP);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        u64_t x0l, x0h, x1l, x1h;
+        lds_2x64(xa0 + 128u * j, x0l, x0h);
+        lds_2x64(xa1 + 128u * j, x1l, x1h);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          glo[k][j] = ffma2(dd[k][0], x0l, glo[k][j]);
+          ghi[k][j] = ffma2(dd[k][0], x0h, ghi[k][j]);
+          glo[k][j] = ffma2(dd[k][1], x1l, glo[k][j]);
+          ghi[k][j] = ffma2(dd[k][1], x1h, ghi[k][j]);
+        }
+      }
+      ge.x = fmaf(de0, xe0.x, fmaf(de1, xe1.x, ge.x));
+      ge.y = fmaf(de0, xe0.y, fmaf(de1, xe1.y, ge.y));
+      ge.z = fmaf(de0, xe0.z, fmaf(de1, xe1.z, ge.z));
+      ge.w = fmaf(de0, xe0.w, fmaf(de1, xe1.w, ge.w));
+    }
+    {                                                  // both passes have read the stage: refill it
+      const long long nt = tile + (long long)NS * GW;
+      __syncwarp();
+      if (nt < ntiles) issue(nt, stage_addr, bar);
+    }
+    if (++buf == NS) {
+      buf = 0;
+      phase ^= 1u;
+    }
+    if (++since_flush >= kSubFlushTiles) {
+      flush();
+      since_flush = 0;
+    }
+  }
+  flush();
+
+  // fixed-order fp64 reduction over the CTA's warps
+  __syncthreads();
+  const double* cta_rows = a.warp_acc + (size_t)blockIdx.x * wpc * NE;
+  double* out = a.cta_part + (size_t)blockIdx.x * NE;
+  for (int e = (BWD ? 0 : a.layout_heads * ctot) + threadIdx.x; e < NE; e += blockDim.x) {
+    double s = 0.0;
+    for (int wv = 0; wv < wpc; ++wv) s += cta_rows[(size_t)wv * NE + e];
+    out[e] = s;
+  }
+}
+
+}  // namespace rfb
