@@ -126,7 +126,8 @@ struct rfb_engine {
   int sweep_staged = 1;   // 1: bulk-async staged rows (cp.async.bulk ring), 0: direct streaming loads
   int sweep_stages = 0;   // depth of each warp's copy ring (0: sized for ~112 KB in flight per SM)
   int sweep_warps = 4;    // warps per CTA
-  int sweep_sub = 1;      // subunit models (several heads on one block) on the subunit sweep (sweep_sub.cuh)
+  int sweep_sub = 3;      // subunit models (several heads on one block) on the subunit sweep (sweep_sub.cuh):
+                          // 0 = off, 3 = default mapping, 1 / 2 = the mappings it was measured against
   int sweep_ctas = -1;    // CTAs per SM (0: as many as fit; -1: auto = 1 for single-head models, where
                           // 4 warps x 3 stages measured best, as many as fit for the compute-heavier multi-head ones)
 };
@@ -184,13 +185,14 @@ struct SweepBuffers {
   int threads = 0;
   int staged = 0, stages = 0;
   size_t smem = 0;
-  bool sub = false;   // this data set runs the subunit sweep
+  int sub = 0;        // this data set runs the subunit sweep: variant (see sub_instance), 0 = no
+  int sub_nj = 0;
 };
 
 // subunit pattern: K heads whose columns are ONE shared block, at most one other head on <= 8 chunks
 struct SubPlan {
   bool ok = false;
-  int slot = 0, K = 0, NJ = 0, c0 = 0;
+  int slot = 0, K = 0, c0 = 0;
   int heads[kSubMaxK] = {};
   int extra_head = -1;
 };
@@ -285,17 +287,29 @@ static SweepFn pick_variant(bool bwd, bool staged, int spec) {
   return pick_staged<H, NCH, RB, 0>(bwd);
 }
 
-template <int K, int NJ>
+template <int K, int NJ, int LPR, bool HOLD>
 static SweepFn pick_sub(bool bwd, int spec) {
   if (spec == 1)
-    return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, true, 1> : (SweepFn)sweep_subunit_kernel<K, NJ, false, 1>;
-  return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, true, 0> : (SweepFn)sweep_subunit_kernel<K, NJ, false, 0>;
+    return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, LPR, HOLD, true, 1>
+               : (SweepFn)sweep_subunit_kernel<K, NJ, LPR, false, false, 1>;
+  return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, LPR, HOLD, true, 0>
+             : (SweepFn)sweep_subunit_kernel<K, NJ, LPR, false, false, 0>;
 }
-static int sub_template_nj(int nj) { return nj <= 3 ? 3 : kSubMaxNJ; }
-static SweepFn sub_instance(int K, int NJ, bool bwd, int spec) {
-#define INST(k, nj) \
-  if (K == k && NJ == nj) return pick_sub<k, nj>(bwd, spec);
-  INST(2, 3) INST(3, 3) INST(4, 3) INST(2, 9) INST(3, 9) INST(4, 9)
+// variant 3 (default, all shapes): 16 lanes per row, rows read twice from the stage.  For 4 subunits the two
+// mappings it was measured against are kept: 1 = 8 lanes per row, 2 = 16 lanes per row with the rows held in
+// registers between the passes (profiles/README.md).
+static int sub_lpr(int variant) { return variant == 1 ? 8 : 16; }
+static int sub_template_nj(int variant, int c0) {
+  if (variant == 1) return c0 <= 24 ? 3 : 9;
+  return c0 <= 16 ? 1 : 5;
+}
+static SweepFn sub_instance(int variant, int K, int NJ, bool bwd, int spec) {
+#define INST(v, k, nj, lpr, hold) \
+  if (variant == v && K == k && NJ == nj) return pick_sub<k, nj, lpr, hold>(bwd, spec);
+  INST(1, 4, 3, 8, false) INST(1, 4, 9, 8, false)
+  INST(2, 4, 1, 16, true) INST(2, 4, 5, 16, true)
+  INST(3, 2, 1, 16, false) INST(3, 3, 1, 16, false) INST(3, 4, 1, 16, false)
+  INST(3, 2, 5, 16, false) INST(3, 3, 5, 16, false) INST(3, 4, 5, 16, false)
 #undef INST
   return nullptr;
 }
@@ -386,8 +400,7 @@ static int build_plan(rfb_model* m) {
       }
       sp.slot = s;
       sp.c0 = p.slot_chunk0[s + 1] - p.slot_chunk0[s];
-      sp.NJ = sub_template_nj((sp.c0 + 7) / 8);
-      sp.ok = clean && sp.K >= 2 && sp.K <= kSubMaxK && others <= 1 && sp.c0 <= 8 * kSubMaxNJ &&
+      sp.ok = clean && sp.K >= 2 && sp.K <= kSubMaxK && others <= 1 && sp.c0 <= 72 &&
               p.n_chunks - sp.c0 <= 8 && (others == 1 || p.n_chunks == sp.c0);
       if (sp.ok) p.sub = sp;
     }
@@ -532,17 +545,20 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
   if (p.sub.ok && e->sweep_sub && e->sweep_staged && all_slots) {
     // subunit sweep (sweep_sub.cuh): 8-row tiles, rows stay in the stage through both passes
     const SubPlan& sp = p.sub;
+    int variant = std::min(std::max(e->sweep_sub, 1), 3);
+    if (variant <= 2 && sp.K != 4) variant = 3;        // the comparison variants exist for 4 subunits only
+    const int NJ = sub_template_nj(variant, sp.c0), cpl = sub_lpr(variant) * NJ;
     int st = e->sweep_stages > 0 ? e->sweep_stages : 2;
     int occ = 0;
     size_t smem = 0;
     bool fits = false;
     for (; st >= 2 && !fits; --st) {
-      smem = sweep_sub_smem_bytes(warps, st, p.ctot, sp.K, sp.NJ, sp.c0);
+      smem = sweep_sub_smem_bytes(warps, st, p.ctot, sp.K, cpl, sp.c0);
       fits = true;
       occ = 1 << 30;
       for (int bwd = 0; bwd < 2 && fits; ++bwd) {
         for (int spec = 0; spec < 2 && fits; ++spec) {
-          SweepFn fn = sub_instance(sp.K, sp.NJ, bwd != 0, spec);
+          SweepFn fn = sub_instance(variant, sp.K, NJ, bwd != 0, spec);
           if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no subunit sweep instance");
           if (smem > 48 * 1024 &&
               cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -573,7 +589,8 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
       sb.staged = 1;
       sb.stages = st;
       sb.smem = smem;
-      sb.sub = true;
+      sb.sub = variant;
+      sb.sub_nj = NJ;
       return RFB_OK;
     }
   }
@@ -649,7 +666,7 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
     int spec = (m->distr == RFB_DISTR_POISSON && eff_out_nl == RFB_NL_SOFTPLUS) ? 1 : 0;
     for (int k = 0; k < p.sub.K; ++k)
       if (head_nl[p.sub.heads[k]] != RFB_NL_SOFTPLUS) spec = 0;
-    fn = sub_instance(p.sub.K, p.sub.NJ, bwd, spec);
+    fn = sub_instance(sb.sub, p.sub.K, sb.sub_nj, bwd, spec);
     if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no subunit sweep instance");
   } else if (!p.generic) {
     fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, sweep_spec(m, head_nl), &RB);

@@ -26,33 +26,34 @@
 
 namespace rfb {
 
-constexpr int kSubRows = 8;      // rows per tile: 2 passes x 4 row groups
+constexpr int kSubRows = 8;      // rows per tile: (32 / LPR) row groups x passes
 constexpr int kSubMaxK = 4;      // subunit heads
-constexpr int kSubMaxNJ = 9;     // chunks per lane: up to 72 chunks = 288 columns in the shared block
+constexpr int kSubMaxChunks = 80;   // chunks of the shared block (LPR x NJ <= 80: 320 columns)
 constexpr int kSubFlushTiles = 64;
 
 // Shared memory.  A stage = the 8-row tile of every design block, 32 B of responses and a zero pad: lane l8
 // reads the chunks l8 + 8 j, j < NJ, of its rows with compile-time offsets; the chunk slots past the block's
 // C0 chunks have zero weights and read on into the next row / block / responses / pad -- finite data that
 // the pad keeps inside the stage.  Then the mbarriers, then the weights [K][8 NJ] float4 (zero past C0).
-__host__ __device__ inline size_t sweep_sub_stage_bytes(int ctot, int NJ, int c0) {
-  return (size_t)kSubRows * ctot * sizeof(float) + 32 + (size_t)(8 * NJ - c0) * 16;
+// (`cpl` = LPR x NJ: chunk slots per row)
+__host__ __device__ inline size_t sweep_sub_stage_bytes(int ctot, int cpl, int c0) {
+  return (size_t)kSubRows * ctot * sizeof(float) + 32 + (size_t)(cpl - c0) * 16;
 }
-__host__ __device__ inline size_t sweep_sub_w_offset(int warps, int stages, int ctot, int NJ, int c0) {
-  return ((size_t)warps * stages * (sweep_sub_stage_bytes(ctot, NJ, c0) + 8) + 15) & ~(size_t)15;
+__host__ __device__ inline size_t sweep_sub_w_offset(int warps, int stages, int ctot, int cpl, int c0) {
+  return ((size_t)warps * stages * (sweep_sub_stage_bytes(ctot, cpl, c0) + 8) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t sweep_sub_smem_bytes(int warps, int stages, int ctot, int K, int NJ, int c0) {
-  return sweep_sub_w_offset(warps, stages, ctot, NJ, c0) + (size_t)K * 8 * NJ * 16;
+__host__ __device__ inline size_t sweep_sub_smem_bytes(int warps, int stages, int ctot, int K, int cpl, int c0) {
+  return sweep_sub_w_offset(warps, stages, ctot, cpl, c0) + (size_t)K * cpl * 16;
 }
 
 __device__ __forceinline__ void lds_2x64(uint32_t addr, u64_t& lo, u64_t& hi) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
 }
 
-// p[i] = this lane's partial of value i; afterwards every lane of an 8-lane group holds the group's
+// p[i] = this lane's partial of value i; afterwards every lane of an LPR-lane group holds the group's
 // sum of value (lane & (VN - 1)).
-template <int VN>
-__device__ __forceinline__ float transpose_reduce8(float (&p)[VN], int lane) {
+template <int VN, int LPR>
+__device__ __forceinline__ float transpose_reduce_grp(float (&p)[VN], int lane) {
 #pragma unroll
   for (int s = VN / 2; s >= 1; s >>= 1) {
     const bool up = (lane & s) != 0;
@@ -65,19 +66,26 @@ __device__ __forceinline__ float transpose_reduce8(float (&p)[VN], int lane) {
   }
   float v = p[0];
 #pragma unroll
-  for (int m = VN; m < 8; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  for (int m = VN; m < LPR; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
 }
 
 // SPEC 0: run-time nonlinearities / distribution; 1: softplus subunits, softplus output, Poisson
-template <int K, int NJ, bool BWD, int SPEC>
+// LPR lanes per row (8 or 16); HOLD: the rows stay in registers from the forward to the backward pass
+// (the stage goes back to the copy engine after the forward loads) instead of being read twice.
+template <int K, int NJ, int LPR, bool HOLD, bool BWD, int SPEC>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const __grid_constant__ SweepArgs a) {
-  static_assert(K >= 2 && K <= kSubMaxK && NJ >= 1 && NJ <= kSubMaxNJ, "shape");
+  static_assert(K >= 2 && K <= kSubMaxK && NJ >= 1 && LPR * NJ <= kSubMaxChunks, "shape");
+  static_assert(LPR == 8 || LPR == 16, "lanes per row");
   constexpr int RT = kSubRows;
+  constexpr int NRG = 32 / LPR;        // row groups of a warp
+  constexpr int NP = RT / NRG;         // passes per tile
   constexpr int KP = K <= 2 ? 2 : 4;   // heads padded to a power of two
-  constexpr int VN = 2 * KP;           // (head, pass) values per row group
+  constexpr int VN = NP * KP;          // (head, pass) values per row group
+  static_assert(VN <= LPR, "one epilogue lane per (head, pass)");
+  constexpr bool KEEP = HOLD && BWD;
   extern __shared__ __align__(128) unsigned char sweep_smem[];
-  const int lane = threadIdx.x & 31, l8 = lane & 7, rg = lane >> 3;
+  const int lane = threadIdx.x & 31, l8 = lane & (LPR - 1), rg = lane / LPR;
   const int wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const long long gw = (long long)blockIdx.x * wpc + wic;
   const long long GW = (long long)gridDim.x * wpc;
@@ -85,20 +93,21 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
   const int NE = a.layout_heads * ctot + kNumScalars;
   const int NS = a.n_stages;
   const int S = a.sub_slot, cs0 = a.slot_chunk0[S], C0 = a.slot_chunk0[S + 1] - cs0;
-  const uint32_t stage_bytes = (uint32_t)sweep_sub_stage_bytes(ctot, NJ, C0);
+  const uint32_t stage_bytes = (uint32_t)sweep_sub_stage_bytes(ctot, LPR * NJ, C0);
   const uint32_t y_off = (uint32_t)(RT * ctot * sizeof(float));
   const uint32_t ldS = (uint32_t)(a.slot_ld[S] * sizeof(float));
 
   const uint32_t sbase = smem_u32(sweep_smem);
   const uint32_t wbase = sbase + (uint32_t)wic * NS * stage_bytes;
   const uint32_t bbase = sbase + (uint32_t)wpc * NS * stage_bytes + (uint32_t)wic * NS * 8u;
-  const uint32_t wsm = sbase + (uint32_t)sweep_sub_w_offset(wpc, NS, ctot, NJ, C0);
-  constexpr uint32_t wstride = 8u * NJ * 16u;
+  const uint32_t wsm = sbase + (uint32_t)sweep_sub_w_offset(wpc, NS, ctot, LPR * NJ, C0);
+  constexpr uint32_t wstride = (uint32_t)LPR * NJ * 16u;
+  constexpr uint32_t jstep = (uint32_t)LPR * 16u;
   const uint32_t wl8 = wsm + (uint32_t)l8 * 16u;
 
   // ---- head weights -> shared memory -----------------------------------------------------------------
-  for (int idx = threadIdx.x; idx < K * 8 * NJ; idx += blockDim.x) {
-    const int k = idx / (8 * NJ), c = idx - k * (8 * NJ);
+  for (int idx = threadIdx.x; idx < K * LPR * NJ; idx += blockDim.x) {
+    const int k = idx / (LPR * NJ), c = idx - k * (LPR * NJ);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C0) v = *reinterpret_cast<const float4*>(a.W + (size_t)a.sub_head[k] * ctot + 4 * (cs0 + c));
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wsm + (uint32_t)idx * 16u), "f"(v.x), "f"(v.y),
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
                  : "memory");
   }
 
-  // the other head: lane l8 owns chunk l8 of the remaining columns (at most 8 chunks)
+  // the other head: lane l8 of a row's lanes owns chunk l8 of the remaining columns (at most 8 chunks)
   const int E = a.n_chunks - C0;
   const int he = a.sub_extra_head;
   uint32_t eoff = (uint32_t)(RT * 16 * cs0), estride = ldS;
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
   const int my_idx = l8 & (VN - 1);
   const int my_k = my_idx % KP, my_p = my_idx / KP;
   const bool head_ok = my_k < K;
-  const bool lane_counts = l8 < VN;                 // K <= 2: lanes 4..7 of a group are duplicates
+  const bool lane_counts = l8 < VN;                 // K <= 2: the upper half of a group's lanes are duplicates
   const int my_head = head_ok ? a.sub_head[my_k] : 0;
   const float hic_lane = head_ok ? a.head_icpt[my_head] : 0.f;
   const int kind_lane = head_ok ? a.head_nl[my_head] : RFB_NL_NONE;
@@ -201,12 +210,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
           unpack2(glo[k][j], v[0], v[1]);
           unpack2(ghi[k][j], v[2], v[3]);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {               // the 4 row groups hold partial sums of the same columns
-            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
-            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+          for (int q = 0; q < 4; ++q) {               // the row groups hold partial sums of the same columns
+#pragma unroll
+            for (int m = LPR; m < 32; m <<= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], m);
           }
-          if (rg == (j & 3) && l8 + 8 * j < C0) {
-            double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)a.sub_head[k] * ctot + 4 * (cs0 + l8 + 8 * j));
+          if (rg == (j % NRG) && l8 + LPR * j < C0) {
+            double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)a.sub_head[k] * ctot + 4 * (cs0 + l8 + LPR * j));
             double2 lo = p2[0], hi = p2[1];
             lo.x += (double)v[0]; lo.y += (double)v[1];
             hi.x += (double)v[2]; hi.y += (double)v[3];
@@ -219,8 +228,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
       float v[4] = {ge.x, ge.y, ge.z, ge.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
-        v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);
+#pragma unroll
+        for (int m = LPR; m < 32; m <<= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], m);
       }
       if (rg == 0 && ecol >= 0) {
         double2* p2 = reinterpret_cast<double2*>(my_acc + (size_t)he * ctot + ecol);
@@ -251,67 +260,91 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
     }
   };
 
+  // Row and weight reads are ordinary shared-memory loads (not volatile asm): the compiler may move them
+  // and the arithmetic between the shuffles (measured: 275 -> 288 it/s at config 4).  The barrier waits
+  // and the copy issue are asm statements with memory clobbers, so no load crosses them.
+  const unsigned char* const smem_gen = sweep_smem;
+  auto ld2 = [&](uint32_t off, u64_t& lo, u64_t& hi) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(smem_gen + off);
+    lo = v.x;
+    hi = v.y;
+  };
   const uint32_t xlane = (uint32_t)(RT * 16 * cs0) + (uint32_t)rg * ldS + (uint32_t)l8 * 16u;
-  int since_flush = 0;
-  int buf = 0;
-  uint32_t phase = 0;
-  for (long long tile = gw; tile < ntiles; tile += GW) {
-    const uint32_t stage_addr = wbase + (uint32_t)buf * stage_bytes;
-    const uint32_t bar = bbase + 8u * (uint32_t)buf;
-    mbar_wait_a(bar, phase);
-    const uint32_t xa0 = stage_addr + xlane;          // pass 0: row rg, chunk l8
-    const uint32_t xa1 = xa0 + 4u * ldS;              // pass 1: row 4 + rg
+  const uint32_t wl8o = wl8 - sbase;
 
-    // ---- forward: per (head, pass) packed partial dot products over this lane's chunks ----------------
-    u64_t acc[K][2];
+  // forward products of the tile in the stage at byte offset `so`: per (head, pass) partial dot products of
+  // this lane's chunks -> pv, the other head's -> ae; the response of this lane's epilogue row -> yv
+  auto fwd_products = [&](uint32_t so, float (&pv)[VN], float (&ae)[NP], float4 (&xe)[NP], float& yv,
+                          u64_t (&xl)[KEEP ? NP : 1][KEEP ? NJ : 1], u64_t (&xh)[KEEP ? NP : 1][KEEP ? NJ : 1]) {
+    u64_t acc[K][NP];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k][0] = acc[k][1] = 0ull;
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) acc[k][p] = 0ull;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      u64_t x0l, x0h, x1l, x1h;
-      lds_2x64(xa0 + 128u * j, x0l, x0h);
-      lds_2x64(xa1 + 128u * j, x1l, x1h);
+      u64_t tl[NP], th[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        ld2(so + xlane + (uint32_t)(p * NRG) * ldS + jstep * j, tl[p], th[p]);
+        if (KEEP) {
+          xl[p][j] = tl[p];
+          xh[p][j] = th[p];
+        }
+      }
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         u64_t wl, wh;
-        lds_2x64(wl8 + (uint32_t)k * wstride + 128u * j, wl, wh);
-        acc[k][0] = ffma2(x0l, wl, acc[k][0]);
-        acc[k][1] = ffma2(x1l, wl, acc[k][1]);
-        acc[k][0] = ffma2(x0h, wh, acc[k][0]);
-        acc[k][1] = ffma2(x1h, wh, acc[k][1]);
+        ld2(wl8o + (uint32_t)k * wstride + jstep * j, wl, wh);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[k][p] = ffma2(tl[p], wl, acc[k][p]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[k][p] = ffma2(th[p], wh, acc[k][p]);
       }
     }
-    const float4 xe0 = lds_f4(stage_addr + eoff + (uint32_t)rg * estride);
-    const float4 xe1 = lds_f4(stage_addr + eoff + (uint32_t)(4 + rg) * estride);
-    float ae0 = fmaf(xe0.x, we.x, fmaf(xe0.y, we.y, fmaf(xe0.z, we.z, xe0.w * we.w)));
-    float ae1 = fmaf(xe1.x, we.x, fmaf(xe1.y, we.y, fmaf(xe1.z, we.z, xe1.w * we.w)));
-    float yv = 0.f;
-    if (has_y) yv = lds_f1(stage_addr + y_off + 4u * (uint32_t)(my_p * 4 + rg));
-
-    float pv[VN];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      xe[p] = *reinterpret_cast<const float4*>(smem_gen + so + eoff + (uint32_t)(p * NRG + rg) * estride);
+      ae[p] = fmaf(xe[p].x, we.x, fmaf(xe[p].y, we.y, fmaf(xe[p].z, we.z, xe[p].w * we.w)));
+    }
+    yv = 0.f;
+    if (has_y) yv = *reinterpret_cast<const float*>(smem_gen + so + y_off + 4u * (uint32_t)(my_p * NRG + rg));
 #pragma unroll
     for (int i = 0; i < VN; ++i) pv[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
+      for (int p = 0; p < NP; ++p) {
         float lo, hi;
         unpack2(acc[k][p], lo, hi);
         pv[k + KP * p] = lo + hi;
       }
     }
-    const float tot = transpose_reduce8<VN>(pv, lane);
-    float aet;
-    {
-      const bool up = (l8 & KP) != 0;                  // == my_p
-      aet = (up ? ae1 : ae0) + __shfl_xor_sync(0xffffffffu, up ? ae0 : ae1, KP);
-#pragma unroll
-      for (int m = 1; m < 8; m <<= 1)
-        if (m != KP) aet += __shfl_xor_sync(0xffffffffu, aet, m);
-    }
+  };
 
-    // ---- epilogue, lane = (row group, pass, head) -------------------------------------------------------
-    const long long myrow = tile * RT + my_p * 4 + rg;
+  // the cross-lane sums: this lane's (head, pass) dot product and the other head's of its pass
+  auto fwd_reduce = [&](float (&pv)[VN], float (&ae)[NP], float& tot, float& aet) {
+    tot = transpose_reduce_grp<VN, LPR>(pv, lane);
+#pragma unroll
+    for (int s = NP / 2; s >= 1; s >>= 1) {
+      const bool up = (l8 & (s * KP)) != 0;
+#pragma unroll
+      for (int j = 0; j < s; ++j) {
+        const float keep = up ? ae[j + s] : ae[j];
+        const float send = up ? ae[j] : ae[j + s];
+        ae[j] = keep + __shfl_xor_sync(0xffffffffu, send, s * KP);
+      }
+    }
+    aet = ae[0];
+#pragma unroll
+    for (int m = 1; m < LPR; m <<= 1)
+      if (m < KP || m >= NP * KP) aet += __shfl_xor_sync(0xffffffffu, aet, m);
+  };
+
+  // epilogue with lane = (row group, pass, head), then the gradient products of the tile
+  auto epilogue_backward = [&](uint32_t so, long long tile, float tot, float aet, float yv, const float4 (&xe)[NP],
+                               u64_t (&xl)[KEEP ? NP : 1][KEEP ? NJ : 1], u64_t (&xh)[KEEP ? NP : 1][KEEP ? NJ : 1]) {
+    const long long myrow = tile * RT + my_p * NRG + rg;
     const bool rowok = myrow < a.n_rows;
     if (!rowok) yv = 0.f;
     float f, dphi;
@@ -320,7 +353,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
 #pragma unroll
     for (int m = 1; m < KP; m <<= 1) u += __shfl_xor_sync(0xffffffffu, u, m);
     float fe, dpe;
-    nl_eval(kind_e, aet + hic_e, fe, dpe);             // warp-uniform kind
+    if (SPEC == 1) {                                   // the other head is linear (or absent): no branch
+      fe = kind_e == RFB_NL_NONE ? aet + hic_e : 0.f;
+      dpe = kind_e == RFB_NL_NONE ? 1.f : 0.f;
+    } else {
+      nl_eval(kind_e, aet + hic_e, fe, dpe);           // warp-uniform kind
+    }
     u += fe;
     u += gic;
     float r, dr;
@@ -360,42 +398,62 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
     if (lane_counts && !(sm_out && kind_lane == RFB_NL_NONE)) sc_head += delta_k;
     if (count_row && !(sm_out && kind_e == RFB_NL_NONE)) sc_e += delta_e;
 
-    // ---- backward: G_k += delta_k x, rows read from the stage a second time -----------------------------
+    // backward: G_k += delta_k x, pass by pass (rows from registers, or read again from the stage)
     if (BWD) {
-      u64_t dd[K][2];
+      if (!KEEP) asm volatile("" ::: "memory");        // read the rows again, do not carry them in registers
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const float d = __shfl_sync(0xffffffffu, delta_k, (lane & 24) | (k + KP * p));
-          dd[k][p] = pack2(d, d);
-        }
-      }
-      const float de0 = __shfl_sync(0xffffffffu, delta_e, lane & 24);
-      const float de1 = __shfl_sync(0xffffffffu, delta_e, (lane & 24) | KP);
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        u64_t x0l, x0h, x1l, x1h;
-        lds_2x64(xa0 + 128u * j, x0l, x0h);
-        lds_2x64(xa1 + 128u * j, x1l, x1h);
+      for (int p = 0; p < NP; ++p) {
+        u64_t dd[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          glo[k][j] = ffma2(dd[k][0], x0l, glo[k][j]);
-          ghi[k][j] = ffma2(dd[k][0], x0h, ghi[k][j]);
-          glo[k][j] = ffma2(dd[k][1], x1l, glo[k][j]);
-          ghi[k][j] = ffma2(dd[k][1], x1h, ghi[k][j]);
+          const float d = __shfl_sync(0xffffffffu, delta_k, (lane & ~(LPR - 1)) | (k + KP * p));
+          dd[k] = pack2(d, d);
         }
+        const float de = __shfl_sync(0xffffffffu, delta_e, (lane & ~(LPR - 1)) | (KP * p));
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          u64_t tl, th;
+          if (KEEP) {
+            tl = xl[p][j];
+            th = xh[p][j];
+          } else {
+            ld2(so + xlane + (uint32_t)(p * NRG) * ldS + jstep * j, tl, th);
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            glo[k][j] = ffma2(dd[k], tl, glo[k][j]);
+            ghi[k][j] = ffma2(dd[k], th, ghi[k][j]);
+          }
+        }
+        ge.x = fmaf(de, xe[p].x, ge.x);
+        ge.y = fmaf(de, xe[p].y, ge.y);
+        ge.z = fmaf(de, xe[p].z, ge.z);
+        ge.w = fmaf(de, xe[p].w, ge.w);
       }
-      ge.x = fmaf(de0, xe0.x, fmaf(de1, xe1.x, ge.x));
-      ge.y = fmaf(de0, xe0.y, fmaf(de1, xe1.y, ge.y));
-      ge.z = fmaf(de0, xe0.z, fmaf(de1, xe1.z, ge.z));
-      ge.w = fmaf(de0, xe0.w, fmaf(de1, xe1.w, ge.w));
     }
-    {                                                  // both passes have read the stage: refill it
-      const long long nt = tile + (long long)NS * GW;
-      __syncwarp();
-      if (nt < ntiles) issue(nt, stage_addr, bar);
-    }
+  };
+
+  auto refill = [&](long long tile, int buf) {         // hand the stage to the copy engine for tile + NS * GW
+    const long long nt = tile + (long long)NS * GW;
+    __syncwarp();
+    if (nt < ntiles) issue(nt, wbase + (uint32_t)buf * stage_bytes, bbase + 8u * (uint32_t)buf);
+  };
+  const uint32_t wbo = wbase - sbase;                  // this warp's ring, as an offset into shared memory
+
+  int since_flush = 0;
+  int buf = 0;
+  uint32_t phase = 0;
+  for (long long tile = gw; tile < ntiles; tile += GW) {
+    const uint32_t so = wbo + (uint32_t)buf * stage_bytes;
+    mbar_wait_a(bbase + 8u * (uint32_t)buf, phase);
+    float pv[VN], ae[NP], yv, tot, aet;
+    float4 xe[NP];
+    u64_t xl[KEEP ? NP : 1][KEEP ? NJ : 1], xh[KEEP ? NP : 1][KEEP ? NJ : 1];
+    fwd_products(so, pv, ae, xe, yv, xl, xh);
+    if (KEEP || !BWD) refill(tile, buf);             // the rows are in registers
+    fwd_reduce(pv, ae, tot, aet);
+    epilogue_backward(so, tile, tot, aet, yv, xe, xl, xh);
+    if (BWD && !KEEP) refill(tile, buf);             // both passes have read the stage
     if (++buf == NS) {
       buf = 0;
       phase ^= 1u;

@@ -657,3 +657,59 @@ def test_generic_sweep_many_subunits(out_nl):
               verbose=0, tolerance=0)
     assert len(g.filter_names) == 8
     _compare_fit(g, o, True)
+
+
+# ---- subunit sweep (csrc/sweep_sub.cuh): shapes around its chunk mapping, against the oracle and against
+# the row-per-warp kernels it replaces ------------------------------------------------------------------------
+@pytest.mark.parametrize("dims,df,subunits,history,filt_nl,out_nl,distr", [
+    ([10, 8, 8], [8, 6, 6], 4, True, "softplus", "softplus", "poisson"),   # config 4's 288 + 8 columns
+    ([8, 6, 6], [5, 4, 4], 3, True, "softplus", "softplus", "poisson"),    # 80 columns: partly used chunk slots
+    ([8, 5, 4], [4, 3, 3], 2, False, "tanh", "none", "gaussian"),          # 36 columns, no other head
+    ([8, 6, 6], [5, 5, 3], 4, True, "sigmoid", "exponential", "poisson"),  # 75 columns (padded to 76)
+])
+def test_subunit_sweep_shapes(dims, df, subunits, history, filt_nl, out_nl, distr):
+    from rfest_b200.engine import Engine
+
+    n = 1237                      # not a multiple of the 8-row tile
+    stim, y, _ = helpers.lnp_data(n, tuple(dims), seed=5)
+    if distr == "gaussian":
+        y = (y - y.mean()).astype(np.float32)
+    results = {}
+    for variant in (3, 0):        # subunit sweep, row-per-warp kernels
+        Engine.get().set_option("sweep_sub", variant)
+        try:
+            g, o = _pair(distr, out_nl)
+            for m in (g, o):
+                m.add_design_matrix(stim, dims=dims, df=df, smooth="cr", filter_nonlinearity=filt_nl, name="stimulus")
+                if history:
+                    m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+                m.initialize(num_subunits=subunits, method="random", random_seed=3)
+                m.alpha, m.beta = 0.5, 0.01
+            _same_p0([o, g], scale=0.2, icpt=0.03)
+            for k, name in enumerate(o.filter_names):
+                bump = (0.05 * np.random.default_rng(900 + k).standard_normal(np.asarray(o.p0[name]).shape)).astype(np.float32)
+                o.p0[name] = o.p0[name] + bump
+                g.p0[name] = (g.p0[name] + bump).astype(np.float32)
+            for m in (g, o):
+                m.y["train"] = np.asarray(y)[m.burn_in:].astype(m.dtype)
+            g._dirty = True
+            lg, gg = g.value_and_grad(g.p0, "train")
+            r = np.asarray(g.forwardpass(g.p0, "train"))
+            results[variant] = (lg, gg, r)
+        finally:
+            Engine.get().set_option("sweep_sub", 3)
+        if variant == 3:
+            lo, go = o.value_and_grad(o.p0, "train")
+            assert abs(lg - lo) < 1e-6 * abs(lo)
+            for name in o.filter_names:
+                scale = np.abs(go[name]).max()
+                assert np.abs(gg[name] - go[name]).max() < 2e-5 * scale
+                assert abs(gg["intercept"][name] - go["intercept"][name]) < 2e-5 * max(1.0, abs(go["intercept"][name]))
+            assert abs(gg["intercept"]["global"] - go["intercept"]["global"]) < 2e-5 * max(
+                1.0, abs(go["intercept"]["global"]))
+            assert _wrel(r, o.forwardpass(o.p0, "train")) < 1e-6
+    (l3, g3, r3), (l0, g0, r0) = results[3], results[0]
+    assert abs(l3 - l0) < 1e-6 * abs(l0) and _wrel(r3, r0) < 1e-6
+    for name in g3:
+        if name != "intercept":
+            assert np.abs(g3[name] - g0[name]).max() < 2e-5 * np.abs(g0[name]).max()
