@@ -91,7 +91,9 @@ int rfb_engine_launch_count(rfb_engine* e, int64_t* out);
 /* Launch-shape knobs of the sweep kernel, applied to models (re)planned afterwards:
  * "sweep_staged" (1 = rows staged through shared memory by cp.async.bulk, 0 = direct loads),
  * "sweep_stages" (ring depth per warp), "sweep_warps" (warps per CTA), "sweep_ctas" (CTAs per
- * SM, 0 = as many as fit).  Also read from RFB_SWEEP_* environment variables at creation. */
+ * SM, 0 = as many as fit), "sweep_sub" (subunit models on the subunit sweep: 3 = default mapping,
+ * 0 = off, 1 / 2 = the mappings it was measured against).  Also read from RFB_SWEEP_* environment
+ * variables at creation. */
 int rfb_engine_set_option(rfb_engine* e, const char* key, int value);
 /* the engine's CUDA stream (cudaStream_t as an integer), for event timing by the caller */
 int rfb_engine_stream(rfb_engine* e, uint64_t* out);

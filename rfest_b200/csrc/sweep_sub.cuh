@@ -7,19 +7,21 @@
 // per row (62 forward + 62 backward FFMA, 31 for the transposed reductions, 30 for one epilogue chain per
 // 4 rows ...) against a budget of ~200 issue slots per row at HBM speed -- instruction-bound at half the
 // HBM rate (profiles/README.md).  This kernel changes the mapping instead of the arithmetic:
-//   * a row is owned by 8 lanes (lane l8 holds the float4 chunks l8, l8 + 8, ...), a warp works on
-//     4 rows at a time and a tile is 2 such passes (8 rows): a (head, row) dot product is reduced over 8
-//     lanes, the 4 heads x 2 passes of a lane's rows by ONE transposed butterfly of 7 shuffles;
-//   * the head weights live in shared memory (one 128-byte broadcast LDS per head and chunk serves all
-//     4 row groups and both passes) -- registers hold only the gradient accumulators, so no columns
-//     are padded to the warp width (288 columns = 9 chunks per lane exactly);
+//   * a row is owned by LPR = 16 lanes (lane l holds the float4 chunks l, l + 16, ...), a warp works on
+//     2 rows at a time and a tile is 4 such passes (8 rows): a (head, row) dot product is reduced over 16
+//     lanes, the 4 heads x 4 passes of a lane's rows by ONE transposed butterfly of 15 shuffles;
+//   * the head weights live in shared memory (one broadcast LDS.128 per head and chunk serves both row
+//     groups and all passes) -- registers hold only the gradient accumulators, so no columns are padded
+//     to the warp width (288 columns = 4.5 chunks per lane);
 //   * products are packed (fma.rn.f32x2): the 8-byte halves of a chunk against the same halves of the
 //     weights forward, (delta, delta) against the chunk backward;
 //   * the rows are read from the shared-memory stage twice (forward, backward) instead of being held;
 //   * the epilogue runs once per tile with lane = (row group, pass, head): all 32 lanes evaluate one
 //     filter nonlinearity each.
-// About 75 warp instructions per row for 4 subunits + history.  Same staging (per-warp ring of bulk-async
-// copies), same accumulator layout, same fixed-order fp64 reductions as sweep.cuh: bit-reproducible.
+// About 115 warp instructions per row for 4 subunits + history (was 250).  Same staging (per-warp ring of
+// bulk-async copies), same accumulator layout, same fixed-order fp64 reductions as sweep.cuh:
+// bit-reproducible.  Measurements and the mappings that lost (8 lanes per row, rows held in registers,
+// a software-pipelined loop): profiles/sweep_sub_r1_ncu.txt, DESIGN.md section 3.2b.
 #pragma once
 
 #include "sweep.cuh"
