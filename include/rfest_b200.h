@@ -165,6 +165,9 @@ int rfb_model_add_filter(rfb_model* m, int slot, int filter_nl, int n_coef);
  * it, rfest/loss.py:15), sum y and sum y^2 are all-reduced over the communicator here. */
 int rfb_model_set_data(rfb_model* m, int kind, int n_slots, rfb_block* const* blocks,
                        const float* y, int y_on_device, int64_t n);
+/* Replace the response of an already bound data set (same n): what a second `fit(y=...)` on the same
+ * design needs -- blocks, plan and scratch stay as they are, the device copy of y is reused. */
+int rfb_model_set_y(rfb_model* m, int kind, const float* y, int y_on_device, int64_t n);
 /* Parameters: b = concatenated filter coefficients (filter order), intercepts = one per
  * filter followed by the global one (p0 of _initialize_p0, _glm.py:369-393). */
 int rfb_model_set_params(rfb_model* m, const float* b, const double* intercepts);
@@ -239,6 +242,10 @@ int rfb_fit_predictions(rfb_model* m, int kind, float* r_out);
 /* The same predictions without leaving the device: pointer to n floats (padded to a multiple of 4),
  * valid until the next forward pass over that data set. */
 int rfb_fit_predictions_ptr(rfb_model* m, int kind, uint64_t* dptr, int64_t* n);
+/* Zero-copy hand-over: trade the storage of block `b` ([ceil((n + 4) / 4) x 4] floats) with the prediction
+ * buffer of `kind`, so that `b` holds the predictions and the model keeps b's old storage for the next
+ * forward pass (y_pred['opt'][kind] of _glm.py:832-834 without an allocation or a copy per fit). */
+int rfb_fit_predictions_swap(rfb_model* m, int kind, rfb_block* b);
 /* Release graph / traces. */
 int rfb_fit_end(rfb_model* m);
 

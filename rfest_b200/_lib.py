@@ -80,6 +80,8 @@ SIGNATURES = {
     "rfb_fit_params_all": (_i, [_p, _i, _p, _p]),
     "rfb_fit_predictions": (_i, [_p, _i, _p]),
     "rfb_fit_predictions_ptr": (_i, [_p, _i, C.POINTER(_u64), C.POINTER(_i64)]),
+    "rfb_fit_predictions_swap": (_i, [_p, _i, _p]),
+    "rfb_model_set_y": (_i, [_p, _i, _p, _i, _i64]),
     "rfb_fit_end": (_i, [_p]),
 }
 

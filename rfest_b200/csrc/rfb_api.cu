@@ -177,6 +177,10 @@ struct DataSet {
 };
 
 
+// floats in a data set's prediction buffer: n + 4 rounded up to whole float4 rows (a [rows x 4] block of the
+// same capacity can trade storage with it, rfb_fit_predictions_swap)
+static inline size_t r_buf_floats(int64_t n) { return ((size_t)n + 4 + 3) / 4 * 4; }
+
 struct SweepBuffers {
   double* warp_acc = nullptr;
   double* cta_part = nullptr;
@@ -742,7 +746,7 @@ static int allreduce_device_f64(rfb_engine* e, double* d, size_t count);
 // calls this before it captures the iteration.
 static int ensure_softmax_buffers(rfb_model* m, int kind) {
   DataSet& ds = m->data[kind];
-  if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * ((size_t)ds.n + 4)));
+  if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * r_buf_floats(ds.n)));
   if (!m->sm_scal[kind]) {
     CU(cudaMalloc(&m->sm_scal[kind], sizeof(double) * 3));
     CU(cudaMalloc(&m->sm_part[kind], sizeof(double) * 2 * kSoftmaxBlocks));
@@ -1383,6 +1387,40 @@ extern "C" int rfb_model_add_filter(rfb_model* m, int slot, int filter_nl, int n
   return (int)m->filters.size() - 1;
 }
 
+// Upload the response of a bound data set (padded by 8 zero floats: the staged sweeps copy the responses of
+// a tile as one 32-byte chunk) and reduce n, sum y, sum y^2 over the communicator.  Reuses the device copy.
+static int upload_y(rfb_model* m, DataSet& ds, const float* y, int y_on_device) {
+  rfb_engine* e = m->e;
+  const int64_t n = ds.n;
+  double mom[3] = {(double)n, 0.0, 0.0};
+  if (y) {
+    if (!ds.y) {
+      CU(cudaMalloc(&ds.y, sizeof(float) * ((size_t)n + 8)));
+      CU(cudaMemsetAsync(ds.y + n, 0, sizeof(float) * 8, e->stream));
+    }
+    CU(cudaMemcpyAsync(ds.y, y, sizeof(float) * (size_t)n,
+                       y_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    ds.has_y = true;
+    const int blocks_y = (int)std::min<int64_t>(512, (n + 255) / 256);
+    TRY(scratch_reserve(e, e->small, sizeof(double) * 2 * 512));
+    y_moments_kernel<<<blocks_y, 256, 0, e->stream>>>(ds.y, n, (double*)e->small.p);
+    e->launches++;
+    CU(cudaGetLastError());
+    std::vector<double> part(2 * blocks_y);
+    CU(cudaMemcpyAsync(part.data(), e->small.p, sizeof(double) * 2 * blocks_y, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < blocks_y; ++k) {
+      mom[1] += part[2 * k];
+      mom[2] += part[2 * k + 1];
+    }
+  }
+  TRY(rfb_engine_allreduce_f64(e, mom, 3));
+  ds.n_total = mom[0];
+  ds.sy = mom[1];
+  ds.syy = mom[2];
+  return RFB_OK;
+}
+
 extern "C" int rfb_model_set_data(rfb_model* m, int kind, int n_slots, rfb_block* const* blocks,
                                   const float* y, int y_on_device, int64_t n) {
   if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
@@ -1421,32 +1459,19 @@ extern "C" int rfb_model_set_data(rfb_model* m, int kind, int n_slots, rfb_block
   cudaFree(m->sb[kind].warp_acc);
   cudaFree(m->sb[kind].cta_part);
   m->sb[kind] = SweepBuffers();
-  double mom[3] = {(double)n, 0.0, 0.0};
-  if (y) {
-    // padded by 8 zero floats: the staged sweep copies the responses of a tile as one 32-byte chunk
-    CU(cudaMalloc(&ds.y, sizeof(float) * ((size_t)n + 8)));
-    CU(cudaMemsetAsync(ds.y + n, 0, sizeof(float) * 8, e->stream));
-    CU(cudaMemcpyAsync(ds.y, y, sizeof(float) * (size_t)n,
-                       y_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
-    ds.has_y = true;
-    const int blocks_y = (int)std::min<int64_t>(512, (n + 255) / 256);
-    TRY(scratch_reserve(e, e->small, sizeof(double) * 2 * 512));
-    y_moments_kernel<<<blocks_y, 256, 0, e->stream>>>(ds.y, n, (double*)e->small.p);
-    e->launches++;
-    CU(cudaGetLastError());
-    std::vector<double> part(2 * blocks_y);
-    CU(cudaMemcpyAsync(part.data(), e->small.p, sizeof(double) * 2 * blocks_y, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    for (int k = 0; k < blocks_y; ++k) {
-      mom[1] += part[2 * k];
-      mom[2] += part[2 * k + 1];
-    }
-  }
-  TRY(rfb_engine_allreduce_f64(e, mom, 3));
-  ds.n_total = mom[0];
-  ds.sy = mom[1];
-  ds.syy = mom[2];
-  return RFB_OK;
+  return upload_y(m, ds, y, y_on_device);
+}
+
+extern "C" int rfb_model_set_y(rfb_model* m, int kind, const float* y, int y_on_device, int64_t n) {
+  if (!m || !y) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  if (m->fit.active) return fail(RFB_ERR_STATE, "cannot rebind data during a fit");
+  DataSet& ds = m->data[kind];
+  if (!ds.bound) return fail(RFB_ERR_STATE, "no data bound for kind %d (rfb_model_set_data first)", kind);
+  if (ds.n != n) return fail(RFB_ERR_INVALID, "y has %lld samples, the bound design %lld", (long long)n, (long long)ds.n);
+  TRY(use_device(m->e));
+  CU(cudaStreamSynchronize(m->e->stream));
+  return upload_y(m, ds, y, y_on_device);
 }
 
 extern "C" int rfb_model_n_params(rfb_model* m, int* n_coef_total, int* n_intercepts) {
@@ -1543,7 +1568,7 @@ static int eval_impl(rfb_model* m, int kind, const float* b, const double* inter
 
   float* d_r = nullptr;
   if (r_out || keep_r) {
-    if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * ((size_t)ds.n + 4)));
+    if (!ds.r_buf) CU(cudaMalloc(&ds.r_buf, sizeof(float) * r_buf_floats(ds.n)));
     d_r = ds.r_buf;
   }
   const bool want_grad = grad_b != nullptr || grad_ic != nullptr;
@@ -2040,8 +2065,8 @@ extern "C" int rfb_fit_finish(rfb_model* m, int i_last) {
   CU(cudaMemcpyAsync(f.it, &it, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   DataSet& tr = m->data[RFB_KIND_TRAIN];
   DataSet& dev = m->data[RFB_KIND_DEV];
-  if (!tr.r_buf) CU(cudaMalloc(&tr.r_buf, sizeof(float) * ((size_t)tr.n + 4)));
-  if (f.has_dev && !dev.r_buf) CU(cudaMalloc(&dev.r_buf, sizeof(float) * ((size_t)dev.n + 4)));
+  if (!tr.r_buf) CU(cudaMalloc(&tr.r_buf, sizeof(float) * r_buf_floats(tr.n)));
+  if (f.has_dev && !dev.r_buf) CU(cudaMalloc(&dev.r_buf, sizeof(float) * r_buf_floats(dev.n)));
   TRY(enqueue_iteration(m, true, tr.r_buf, f.has_dev ? dev.r_buf : nullptr));
   CU(cudaStreamSynchronize(e->stream));
   f.finished = true;
@@ -2120,6 +2145,23 @@ extern "C" int rfb_fit_predictions_ptr(rfb_model* m, int kind, uint64_t* dptr, i
   if (!ds.r_buf) return fail(RFB_ERR_STATE, "no predictions for kind %d", kind);
   *dptr = (uint64_t)(uintptr_t)ds.r_buf;
   *n = ds.n;
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_predictions_swap(rfb_model* m, int kind, rfb_block* b) {
+  if (!m || !b) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind != RFB_KIND_TRAIN && kind != RFB_KIND_DEV) return fail(RFB_ERR_INVALID, "bad kind");
+  Fit& f = m->fit;
+  if (!f.active || !f.finished) return fail(RFB_ERR_STATE, "rfb_fit_finish has not been called");
+  DataSet& ds = m->data[kind];
+  if (!ds.r_buf) return fail(RFB_ERR_STATE, "no predictions for kind %d", kind);
+  if (b->e != m->e) return fail(RFB_ERR_INVALID, "block belongs to another engine");
+  if ((size_t)b->n_rows * (size_t)b->ld != r_buf_floats(ds.n))
+    return fail(RFB_ERR_INVALID, "block holds %lld floats, the prediction buffer %lld",
+                (long long)(b->n_rows * b->ld), (long long)r_buf_floats(ds.n));
+  TRY(use_device(m->e));
+  CU(cudaStreamSynchronize(m->e->stream));
+  std::swap(ds.r_buf, b->d);
   return RFB_OK;
 }
 

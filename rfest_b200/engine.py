@@ -234,6 +234,20 @@ class DeviceVector:
         """Uninitialised vector for a kernel to fill through `device_ptr`."""
         return cls(engine, None, n)
 
+    @classmethod
+    def adopt(cls, block, n, recycle=None):
+        """Vector over an existing [rows x 4] block (no allocation, no copy).  `recycle(block)` is called
+        when the vector is garbage-collected, so the owner can reuse the storage."""
+        v = cls.__new__(cls)
+        v.n = int(n)
+        v.shape = (v.n,)
+        v.dtype = np.dtype(np.float32)
+        v._block = block
+        v._host = None
+        if recycle is not None:
+            weakref.finalize(v, recycle, block)
+        return v
+
     @property
     def device_ptr(self):
         return self._block.device_ptr
@@ -271,6 +285,7 @@ class DeviceModel:
                                         C.byref(h)))
         self.handle = h
         self._keep = {}
+        self._spare = {}         # kind -> spare [rows x 4] blocks for the prediction hand-over
         self._finalizer = weakref.finalize(self, self.lib.rfb_model_destroy, h)
 
     def clear_filters(self):
@@ -288,6 +303,12 @@ class DeviceModel:
         check(self.lib.rfb_model_set_data(self.handle, _lib.KIND[kind], len(blocks), arr, ptr,
                                           on_dev, int(n)))
         self._keep[kind] = list(blocks)      # blocks must outlive the binding
+        del keep
+
+    def set_y(self, kind, y, n):
+        """Replace the response of an already bound data set (rfb_model_set_y)."""
+        ptr, on_dev, keep, _ = as_f32(y)
+        check(self.lib.rfb_model_set_y(self.handle, _lib.KIND[kind], ptr, on_dev, int(n)))
         del keep
 
     def n_params(self):
@@ -400,10 +421,30 @@ class DeviceModel:
         return r
 
     def fit_predictions_device(self, kind):
-        """Predictions of the final forward pass as a DeviceVector (no host copy until asked)."""
+        """Predictions of the final forward pass as a DeviceVector (no host copy until asked).  The vector
+        takes over the model's prediction buffer and the model gets a spare one in exchange
+        (rfb_fit_predictions_swap); vectors that are garbage-collected return their storage to the
+        spares, so repeated fits neither allocate nor copy."""
         ptr, n = C.c_uint64(), C.c_int64()
         check(self.lib.rfb_fit_predictions_ptr(self.handle, _lib.KIND[kind], C.byref(ptr), C.byref(n)))
-        return DeviceVector(self.engine, ptr.value, n.value)
+        rows = (n.value + 4 + 3) // 4
+        spares = self._spare.setdefault(kind, [])
+        blk = None
+        while spares and blk is None:
+            cand = spares.pop()
+            if cand.shape == (rows, 4):
+                blk = cand
+        if blk is None:
+            blk = Block(self.engine, rows, 4)
+        check(self.lib.rfb_fit_predictions_swap(self.handle, _lib.KIND[kind], blk.handle))
+        me = weakref.ref(self)
+
+        def recycle(block, me=me, kind=kind):
+            dm = me()
+            if dm is not None and len(dm._spare.setdefault(kind, [])) < 2:
+                dm._spare[kind].append(block)
+
+        return DeviceVector.adopt(blk, n.value, recycle)
 
     def fit_end(self):
         check(self.lib.rfb_fit_end(self.handle))

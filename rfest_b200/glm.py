@@ -106,6 +106,8 @@ class GLM:
         self.engine = Engine.get(device).init_distributed()
         self._dm = DeviceModel(self.engine, distr, output_nonlinearity)
         self._dirty = True
+        self._y_changed = set()  # kinds whose response alone changed since the last _sync
+        self._synced_y = set()   # kinds whose response the device model holds
         self._blocks = {}        # kind -> name -> Block
         self._n_rows = {}        # kind -> rows owned by this rank
         self._row_range = {}     # kind -> (lo, hi) trimmed rows owned by this rank
@@ -529,7 +531,19 @@ class GLM:
     def _sync(self):
         """(Re)describe filters and data to the device model when something changed."""
         if not self._dirty:
+            # only responses changed (a second fit(y=...) on the same design): keep plan and scratch
+            for kind in sorted(self._y_changed):
+                y = self.y.get(kind)
+                n = self._n_rows.get(kind)
+                if y is None or n is None:
+                    continue
+                if len(y) != n:
+                    raise ValueError(f"`y` for `{kind}` has {len(y)} samples after burn-in, the design has {n}")
+                self._dm.set_y(kind, y, n)
+            self._y_changed.clear()
             return
+        self._y_changed.clear()
+        self._synced_y = set()
         dm = self._dm
         dm.clear_filters()
         train = self._blocks.get("train", {})
@@ -562,6 +576,8 @@ class GLM:
             if y is not None and len(y) != n:
                 raise ValueError(f"`y` for `{kind}` has {len(y)} samples after burn-in, the design has {n}")
             dm.set_data(kind, per_slot, y, n)
+            if y is not None:
+                self._synced_y.add(kind)
         self._dirty = False
 
     def _flatten(self, p):
@@ -810,13 +826,18 @@ class GLM:
             if "train" not in self.y:
                 raise ValueError("No `y` is provided.")                          # _glm.py:896
         else:
+            changed = ["train"]
             if type(y) is dict:
                 self.y["train"] = self._trim_y(y["train"], "train")
                 if "dev" in y:
                     self.y["dev"] = self._trim_y(y["dev"], "dev")
+                    changed.append("dev")
             else:
                 self.y["train"] = self._trim_y(y, "train")
-            self._dirty = True
+            if any(k not in self._synced_y for k in changed):
+                self._dirty = True          # first response of a data set: full (re)description
+            else:
+                self._y_changed.update(changed)
         if self.p0 is None:
             raise ValueError("call initialize() (or set `p0`) before fit()")
         self.y_pred["opt"] = {}

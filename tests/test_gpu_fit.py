@@ -713,3 +713,40 @@ def test_subunit_sweep_shapes(dims, df, subunits, history, filt_nl, out_nl, dist
     for name in g3:
         if name != "intercept":
             assert np.abs(g3[name] - g0[name]).max() < 2e-5 * np.abs(g0[name]).max()
+
+
+def test_refit_with_new_response_keeps_plan_and_old_predictions():
+    """A second fit(y=...) on the same design only replaces the response on the device (rfb_model_set_y) and
+    hands the predictions over without a copy (rfb_fit_predictions_swap): results must equal a fresh model's,
+    and the first fit's y_pred must survive the second fit."""
+    from rfest_b200 import GLM
+
+    n = 2111
+    stim, y1, _ = helpers.lnp_data(n, (8, 5, 4), seed=21)
+    y2 = np.roll(y1, 37).astype(np.float32)
+
+    def fresh(y):
+        m = GLM(distr="poisson", output_nonlinearity="softplus")
+        m.add_design_matrix(stim, dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", name="stimulus")
+        m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(method="random", random_seed=3, compute_ci=False)
+        return m
+
+    kw = dict(num_iters=25, step_size=0.03, beta=0.01, verbose=0, tolerance=0)
+    a = fresh(y1)
+    a.fit(y=y1, **kw)
+    pred1 = a.y_pred["opt"]["train"]
+    pred1_host = np.array(np.asarray(pred1), copy=True)
+    cost1 = a.cost_train.copy()
+    a.fit(y=y2, **kw)                                   # light path: same design, new response
+    assert not a._dirty
+    b = fresh(y1)                                       # same history design as `a`, response y2
+    b.fit(y=y2, **kw)
+    assert np.array_equal(a.cost_train, b.cost_train)
+    assert np.array_equal(np.asarray(a.y_pred["opt"]["train"]), np.asarray(b.y_pred["opt"]["train"]))
+    assert not np.array_equal(cost1, a.cost_train)
+    # the vector handed out by the first fit still holds the first fit's predictions
+    assert np.array_equal(pred1.as_torch().cpu().numpy(), pred1_host)
+    a.fit(y=y1, **kw)                                   # and back: bit-identical to the first fit
+    assert np.array_equal(a.cost_train, cost1)
+    assert np.array_equal(np.asarray(a.y_pred["opt"]["train"]), pred1_host)
