@@ -750,3 +750,31 @@ def test_refit_with_new_response_keeps_plan_and_old_predictions():
     a.fit(y=y1, **kw)                                   # and back: bit-identical to the first fit
     assert np.array_equal(a.cost_train, cost1)
     assert np.array_equal(np.asarray(a.y_pred["opt"]["train"]), pred1_host)
+
+
+def test_subunit_predict_with_and_without_history_block():
+    """predict/score of a subunit model: with both blocks the forward-only subunit sweep runs without a
+    response; with the stimulus alone the history block is absent and the row-per-warp kernels take over."""
+    n = 1800
+    stim, y, _ = helpers.lnp_data(n, (8, 5, 4), seed=17)
+    n_tr = 1400
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr",
+                            filter_nonlinearity="softplus", name="stimulus")
+        m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(num_subunits=3, method="random", random_seed=3)
+    _same_p0([o, g], icpt=0.02)
+    for k, name in enumerate(o.filter_names):            # distinct subunits
+        bump = (0.05 * np.random.default_rng(70 + k).standard_normal(np.asarray(o.p0[name]).shape)).astype(np.float32)
+        o.p0[name] = o.p0[name] + bump
+        g.p0[name] = (g.p0[name] + bump).astype(np.float32)
+    for m in (g, o):
+        m.fit(y=y[:n_tr], num_iters=15, step_size=0.02, beta=0.01, alpha=0.5, verbose=0, tolerance=0)
+    both = {"stimulus": stim[n_tr:], "history": y[n_tr:]}
+    sg, pg = g.score(both, y[n_tr:], return_prediction=True)
+    so, po = o.score(both, y[n_tr:], return_prediction=True)
+    assert _wrel(pg, po) < 1e-4 and abs(sg - so) < 1e-4
+    sg, pg = g.score(stim[n_tr:], y[n_tr:], return_prediction=True)
+    so, po = o.score(stim[n_tr:], y[n_tr:], return_prediction=True)
+    assert _wrel(pg, po) < 1e-4 and abs(sg - so) < 1e-4
