@@ -180,6 +180,10 @@ int rfb_model_n_params(rfb_model* m, int* n_coef_total, int* n_intercepts);
 int rfb_model_eval(rfb_model* m, int kind, const float* b, const double* intercepts,
                    float* r_out, double* sums);
 
+/* cost(p, kind, precomputed=r) (_glm.py:596-603): the loss terms of GIVEN predictions r[n] against the bound
+ * response -- loss_ab = {sum -log(r') y, sum r'} (Poisson) or {sum (y - r)^2, 0} (Gaussian), all-reduced. */
+int rfb_model_loss_of_predictions(rfb_model* m, int kind, const float* r, int r_on_device, double* loss_ab);
+
 /* value_and_grad(cost) of the data term (_glm.py:692-696 without the penalty): the same sums plus
  * d loss / d b [n_coef_total] and d loss / d intercepts [n_intercepts] (filters, then global), float64. */
 int rfb_model_value_and_grad(rfb_model* m, int kind, const float* b, const double* intercepts,

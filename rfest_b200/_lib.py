@@ -82,6 +82,7 @@ SIGNATURES = {
     "rfb_fit_predictions_ptr": (_i, [_p, _i, C.POINTER(_u64), C.POINTER(_i64)]),
     "rfb_fit_predictions_swap": (_i, [_p, _i, _p]),
     "rfb_model_set_y": (_i, [_p, _i, _p, _i, _i64]),
+    "rfb_model_loss_of_predictions": (_i, [_p, _i, _p, _i, C.POINTER(C.c_double)]),
     "rfb_fit_end": (_i, [_p]),
 }
 

@@ -1622,6 +1622,37 @@ extern "C" int rfb_model_eval(rfb_model* m, int kind, const float* b, const doub
   return eval_impl(m, kind, b, intercepts, r_out, sums, nullptr, nullptr);
 }
 
+extern "C" int rfb_model_loss_of_predictions(rfb_model* m, int kind, const float* r, int r_on_device,
+                                            double* loss_ab) {
+  if (!m || !r || !loss_ab) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind < 0 || kind > 2) return fail(RFB_ERR_INVALID, "bad kind %d", kind);
+  DataSet& ds = m->data[kind];
+  if (!ds.bound || !ds.has_y) return fail(RFB_ERR_STATE, "no response bound for kind %d", kind);
+  rfb_engine* e = m->e;
+  TRY(use_device(e));
+  const int64_t n = ds.n;
+  const float* d_r = r;
+  if (!r_on_device) {
+    TRY(scratch_reserve(e, e->stage, sizeof(float) * (size_t)n));
+    CU(cudaMemcpyAsync(e->stage.p, r, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    d_r = (const float*)e->stage.p;
+  }
+  const int blocks = (int)std::min<int64_t>(512, (n + 255) / 256);
+  TRY(scratch_reserve(e, e->small, sizeof(double) * 2 * 512));
+  loss_terms_kernel<<<blocks, 256, 0, e->stream>>>(d_r, ds.y, n, m->distr, (double*)e->small.p);
+  e->launches++;
+  CU(cudaGetLastError());
+  std::vector<double> part(2 * blocks);
+  CU(cudaMemcpyAsync(part.data(), e->small.p, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  loss_ab[0] = loss_ab[1] = 0.0;
+  for (int k = 0; k < blocks; ++k) {
+    loss_ab[0] += part[2 * k];
+    loss_ab[1] += part[2 * k + 1];
+  }
+  return rfb_engine_allreduce_f64(e, loss_ab, 2);
+}
+
 extern "C" int rfb_model_value_and_grad(rfb_model* m, int kind, const float* b, const double* intercepts,
                                         double* sums, double* grad_b, double* grad_icpt) {
   if (!grad_b || !grad_icpt) return fail(RFB_ERR_INVALID, "NULL gradient buffer");

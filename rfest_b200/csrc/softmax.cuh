@@ -59,6 +59,45 @@ softmax_stats_kernel(const float* __restrict__ z, const float* __restrict__ y, l
   }
 }
 
+// Loss terms of given predictions r (GLM.cost(..., precomputed=r), _glm.py:596-603): per block
+// part[2 block] = sum of -log(r') y (Poisson, loss.py:4-10) or (y - r)^2 (Gaussian, loss.py:14-16),
+// part[2 block + 1] = sum of r' (Poisson) -- the same fp32 per-sample terms as the sweeps, fp64 sums.
+__global__ void __launch_bounds__(256)
+loss_terms_kernel(const float* __restrict__ r, const float* __restrict__ y, long long n, int distr, double* part) {
+  __shared__ double sh_a[8], sh_b[8];
+  double acc_a = 0.0, acc_b = 0.0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const float rv = r[t];
+    const float yv = y[t];
+    if (distr == RFB_DISTR_POISSON) {
+      const bool fin = rv != CUDART_INF_F;
+      const float r1 = fin ? rv : 0.f;
+      const float r2 = (r1 != r1) ? r1 : fmaxf(r1, 1e-20f);
+      acc_a += (double)(-logf(r2) * yv);
+      acc_b += (double)r2;
+    } else {
+      const float err = yv - rv;
+      acc_a += (double)(err * err);
+    }
+  }
+  acc_a = warp_sum_f64(acc_a);
+  acc_b = warp_sum_f64(acc_b);
+  if ((threadIdx.x & 31) == 0) {
+    sh_a[threadIdx.x >> 5] = acc_a;
+    sh_b[threadIdx.x >> 5] = acc_b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sa = 0.0, sb = 0.0;
+    for (int k = 0; k < 8; ++k) {
+      sa += sh_a[k];
+      sb += sh_b[k];
+    }
+    part[2 * blockIdx.x] = sa;
+    part[2 * blockIdx.x + 1] = sb;
+  }
+}
+
 // fixed-order sums of the block partials: out = {sum (dL/dr) r, sum r}
 __global__ void softmax_sum_kernel(const double* part, int n_part, double* out) {
   if (threadIdx.x < 2 && blockIdx.x == 0) {

@@ -311,6 +311,17 @@ class DeviceModel:
         check(self.lib.rfb_model_set_y(self.handle, _lib.KIND[kind], ptr, on_dev, int(n)))
         del keep
 
+    def loss_of_predictions(self, kind, r):
+        """-> (loss_a, loss_b) of given predictions against the bound response (rfb_model_loss_of_predictions)."""
+        if isinstance(r, DeviceVector):
+            ptr, on_dev, keep = C.c_void_p(r.device_ptr), 1, r
+        else:
+            ptr, on_dev, keep, _ = as_f32(r)
+        out = (C.c_double * 2)()
+        check(self.lib.rfb_model_loss_of_predictions(self.handle, _lib.KIND[kind], ptr, on_dev, out))
+        del keep
+        return float(out[0]), float(out[1])
+
     def n_params(self):
         a, b = C.c_int(), C.c_int()
         check(self.lib.rfb_model_n_params(self.handle, C.byref(a), C.byref(b)))

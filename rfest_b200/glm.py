@@ -641,14 +641,17 @@ class GLM:
 
     def cost(self, p, kind="train", precomputed=None, penalize=True):
         """_glm.py:573-614."""
-        if precomputed is not None:
-            raise NotImplementedError("`precomputed` forward passes are not supported: the engine "
-                                      "fuses the forward pass into the cost sweep")
         if kind not in self.y:
             raise ValueError(f"No `y` is provided for `{kind}`.")
         self._sync()
         b, ic = self._flatten(p)
-        _, sums = self._dm.eval(kind, b, ic)
+        if precomputed is not None:                                               # _glm.py:596-599
+            if len(precomputed) != self._n_rows[kind]:
+                raise ValueError(f"`precomputed` has {len(precomputed)} samples, `{kind}` has {self._n_rows[kind]}")
+            la, lb = self._dm.loss_of_predictions(kind, precomputed)
+            sums = {_lib.SUM_LOSS_A: la, _lib.SUM_LOSS_B: lb}
+        else:
+            _, sums = self._dm.eval(kind, b, ic)
         loss = self._loss_from_sums(sums, kind)
         if penalize and (self.beta is not None and self.beta != 0) and kind == "train":
             w = b.astype(np.float32)                                              # loss.py:19-23

@@ -778,3 +778,27 @@ def test_subunit_predict_with_and_without_history_block():
     sg, pg = g.score(stim[n_tr:], y[n_tr:], return_prediction=True)
     so, po = o.score(stim[n_tr:], y[n_tr:], return_prediction=True)
     assert _wrel(pg, po) < 1e-4 and abs(sg - so) < 1e-4
+
+
+@pytest.mark.parametrize("distr,out_nl", [("poisson", "softplus"), ("gaussian", "none")])
+def test_cost_with_precomputed_predictions(distr, out_nl):
+    """cost(p, kind, precomputed=r) (_glm.py:596-603): the loss of given predictions, host or device."""
+    stim, y, _ = helpers.lnp_data(1500, (8, 5, 4), seed=4)
+    if distr == "gaussian":
+        y = (y - y.mean()).astype(np.float32)
+    g, o = _pair(distr, out_nl)
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", name="stimulus")
+        m.initialize(method="random", random_seed=1)
+        m.alpha, m.beta = 0.5, 0.01
+    _same_p0([o, g], icpt=0.05)
+    for m in (g, o):
+        m.y["train"] = np.asarray(y)[m.burn_in:].astype(m.dtype)
+    g._dirty = True
+    r = g.forwardpass(g.p0, "train")
+    want = g.cost(g.p0, "train")
+    assert abs(g.cost(g.p0, "train", precomputed=r) - want) < 1e-9 * abs(want)
+    assert abs(g.cost(g.p0, "train", precomputed=np.asarray(r)) - want) < 1e-9 * abs(want)
+    r2 = np.asarray(r) * 1.1 + 0.01
+    wo = o.cost(o.p0, "train", precomputed=r2.astype(np.float64), penalize=False)
+    assert abs(g.cost(g.p0, "train", precomputed=r2.astype(np.float32), penalize=False) - wo) < 1e-6 * abs(wo)
