@@ -33,11 +33,11 @@ constexpr int kSubMaxK = 4;      // subunit heads
 constexpr int kSubMaxChunks = 80;   // chunks of the shared block (LPR x NJ <= 80: 320 columns)
 constexpr int kSubFlushTiles = 64;
 
-// Shared memory.  A stage = the 8-row tile of every design block, 32 B of responses and a zero pad: lane l8
-// reads the chunks l8 + 8 j, j < NJ, of its rows with compile-time offsets; the chunk slots past the block's
-// C0 chunks have zero weights and read on into the next row / block / responses / pad -- finite data that
-// the pad keeps inside the stage.  Then the mbarriers, then the weights [K][8 NJ] float4 (zero past C0).
-// (`cpl` = LPR x NJ: chunk slots per row)
+// Shared memory.  A stage = the 8-row tile of every design block, 32 B of responses and a zero pad: lane l
+// (of a row's LPR lanes) reads the chunks l + LPR j, j < NJ, of its rows with compile-time offsets; the chunk
+// slots past the block's C0 chunks have zero weights and read on into the next row / block / responses /
+// pad -- finite data that the pad keeps inside the stage.  Then the mbarriers, then the weights
+// [K][LPR NJ] float4 (zero past C0).  `cpl` = LPR x NJ: chunk slots per row.
 __host__ __device__ inline size_t sweep_sub_stage_bytes(int ctot, int cpl, int c0) {
   return (size_t)kSubRows * ctot * sizeof(float) + 32 + (size_t)(cpl - c0) * 16;
 }
@@ -46,10 +46,6 @@ __host__ __device__ inline size_t sweep_sub_w_offset(int warps, int stages, int 
 }
 __host__ __device__ inline size_t sweep_sub_smem_bytes(int warps, int stages, int ctot, int K, int cpl, int c0) {
   return sweep_sub_w_offset(warps, stages, ctot, cpl, c0) + (size_t)K * cpl * 16;
-}
-
-__device__ __forceinline__ void lds_2x64(uint32_t addr, u64_t& lo, u64_t& hi) {
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
 }
 
 // p[i] = this lane's partial of value i; afterwards every lane of an LPR-lane group holds the group's
