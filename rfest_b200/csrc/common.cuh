@@ -10,9 +10,9 @@
 namespace rfb {
 
 constexpr int kMaxSlots = 8;    // design blocks bound to one data set
-constexpr int kMaxHeads = 8;    // dot products per row (merged 'none' filters count once); the
-                                // register-resident kernels take up to 5, the generic one up to 8
-constexpr int kNumScalars = 16; // per-sweep scalar sums (8 fixed + one per head, padded)
+constexpr int kMaxHeads = 16;   // dot products per row (merged 'none' filters count once); the
+                                // register-resident kernels take up to 5, the generic one up to 16
+constexpr int kNumScalars = 32; // per-sweep scalar sums (8 fixed + one per head, padded)
 constexpr int kNlAbsent = 100;  // internal nonlinearity code: head without data, contributes 0
 
 // layout of the scalar part of a sweep's accumulator vector

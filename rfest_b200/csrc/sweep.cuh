@@ -782,14 +782,14 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
 }
 
 // ================================================================================================
-// Variant C -- generic fallback: any number of columns, up to 8 heads.  Nothing is kept in
+// Variant C -- generic fallback: any number of columns, up to 16 heads.  Nothing is kept in
 // registers across rows: the head weights are read through L1, and the gradient goes straight
 // into the warp's fp64 accumulator row (L2 resident) once per 4-row tile.  About 3x the memory
 // traffic of the register-resident kernels; used only for shapes those cannot take (e.g. a 3-D
 // filter without a spline basis: 7500 columns).
 // ================================================================================================
 constexpr int kGenRB = 4;
-constexpr int kGenHeads = 8;
+constexpr int kGenHeads = kMaxHeads;
 
 template <bool BWD>
 __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __grid_constant__ SweepArgs a, int H) {

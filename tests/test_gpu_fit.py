@@ -659,6 +659,25 @@ def test_generic_sweep_many_subunits(out_nl):
     _compare_fit(g, o, True)
 
 
+def test_generic_sweep_thirteen_heads():
+    """12 subunits + history = 13 dot products per sample (the generic kernel takes up to 16)."""
+    stim, y, _ = helpers.lnp_data(1500, (8, 5, 4), seed=19)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim[:1200], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity="softplus",
+                            name="stimulus")
+        m.add_design_matrix(stim[1200:], name="stimulus", kind="dev")
+        m.add_design_matrix(y[:1200], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.add_design_matrix(y[1200:], name="history", kind="dev")
+        m.initialize(num_subunits=12, method="random", random_seed=3, compute_ci=False)
+    _same_p0([o, g], scale=0.2, icpt=0.01)
+    for m in (g, o):
+        m.fit(y={"train": y[:1200], "dev": y[1200:]}, num_iters=25, alpha=0.5, beta=0.01, step_size=0.02,
+              verbose=0, tolerance=0)
+    assert len(g.filter_names) == 13
+    _compare_fit(g, o, True)
+
+
 # ---- subunit sweep (csrc/sweep_sub.cuh): shapes around its chunk mapping, against the oracle and against
 # the row-per-warp kernels it replaces ------------------------------------------------------------------------
 @pytest.mark.parametrize("dims,df,subunits,history,filt_nl,out_nl,distr", [
