@@ -821,3 +821,54 @@ def test_cost_with_precomputed_predictions(distr, out_nl):
     r2 = np.asarray(r) * 1.1 + 0.01
     wo = o.cost(o.p0, "train", precomputed=r2.astype(np.float64), penalize=False)
     assert abs(g.cost(g.p0, "train", precomputed=r2.astype(np.float32), penalize=False) - wo) < 1e-6 * abs(wo)
+
+
+def test_subunit_sweep_extreme_drive_matches_row_per_warp_kernels():
+    """Overflowing / vanishing rates (exp overflow in the naive softplus, the 1e-20 clamp of loss.py:5-6):
+    both sweep mappings must take the same branches."""
+    from rfest_b200 import GLM
+    from rfest_b200.engine import Engine
+
+    n = 1500
+    stim, y, _ = helpers.lnp_data(n, (8, 5, 4), seed=23)
+    out = {}
+    for variant in (3, 0):
+        Engine.get().set_option("sweep_sub", variant)
+        try:
+            for scale in (60.0, -60.0):
+                m = GLM(distr="poisson", output_nonlinearity="exponential")
+                m.add_design_matrix(stim, dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity="softplus",
+                                    name="stimulus")
+                m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+                m.initialize(num_subunits=4, method="random", random_seed=3, compute_ci=False)
+                m.alpha, m.beta = 1.0, 0.0
+                p = {name: (np.random.default_rng(5 + k).standard_normal(np.asarray(m.p0[name]).shape)
+                            * (8.0 if name != "history" else 0.1)).astype(np.float32)
+                     for k, name in enumerate(m.filter_names)}
+                p["intercept"] = {k: 0.0 for k in m.p0["intercept"]}
+                p["intercept"]["global"] = scale
+                m.y["train"] = np.asarray(y)[m.burn_in:].astype(np.float32)
+                m._dirty = True
+                loss, g = m.value_and_grad(p, "train", penalize=False)
+                r = np.asarray(m.forwardpass(p, "train"))
+                out[(variant, scale)] = (loss, g, r)
+        finally:
+            Engine.get().set_option("sweep_sub", 3)
+    for scale in (60.0, -60.0):
+        (l3, g3, r3), (l0, g0, r0) = out[(3, scale)], out[(0, scale)]
+        assert np.array_equal(np.isfinite(r3), np.isfinite(r0))
+        fin = np.isfinite(r0)
+        # r = exp(u) with |u| up to ~80: an ulp of u (summation order) is 1e-5 of r
+        assert np.allclose(r3[fin], r0[fin], rtol=3e-4, atol=0)
+        assert np.isfinite(l3) == np.isfinite(l0)
+        if np.isfinite(l0):
+            assert abs(l3 - l0) <= 3e-4 * abs(l0)
+        for name in g0:
+            if name != "intercept":
+                a, b = np.asarray(g3[name]), np.asarray(g0[name])
+                assert np.array_equal(np.isfinite(a), np.isfinite(b))
+                ok = np.isfinite(b)
+                assert np.abs(a[ok] - b[ok]).max() <= 1e-3 * max(np.abs(b[ok]).max(), 1e-30)
+    r_hi, r_lo = out[(0, 60.0)][2], out[(0, -60.0)][2]
+    assert not np.all(np.isfinite(r_hi)) or r_hi.max() > 1e30      # the test reached the overflow branch
+    assert r_lo.min() < 1e-20                                      # and the clamp of loss.py:6
