@@ -872,3 +872,27 @@ def test_subunit_sweep_extreme_drive_matches_row_per_warp_kernels():
     r_hi, r_lo = out[(0, 60.0)][2], out[(0, -60.0)][2]
     assert not np.all(np.isfinite(r_hi)) or r_hi.max() > 1e30      # the test reached the overflow branch
     assert r_lo.min() < 1e-20                                      # and the clamp of loss.py:6
+
+
+@pytest.mark.parametrize("n_raw", [12, 15, 40])
+def test_subunit_sweep_tiny_data_sets(n_raw):
+    """Fewer rows than one 8-row tile (5 after burn-in), exactly one tile, a handful of tiles."""
+    stim, y, _ = helpers.lnp_data(n_raw, (8, 5, 4), seed=3)
+    g, o = _pair("poisson", "softplus")
+    for m in (g, o):
+        m.add_design_matrix(stim, dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity="softplus",
+                            name="stimulus")
+        m.add_design_matrix(y, dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        m.initialize(num_subunits=4, method="random", random_seed=3, compute_ci=False)
+        m.alpha, m.beta = 0.5, 0.01
+    _same_p0([o, g], scale=0.2, icpt=0.03)
+    for m in (g, o):
+        m.y["train"] = np.asarray(y)[m.burn_in:].astype(m.dtype)
+    g._dirty = True
+    assert len(g.y["train"]) == n_raw - 7
+    lg, gg = g.value_and_grad(g.p0, "train")
+    lo, go = o.value_and_grad(o.p0, "train")
+    assert abs(lg - lo) < 1e-6 * abs(lo)
+    for name in o.filter_names:
+        assert np.abs(gg[name] - go[name]).max() < 2e-5 * max(np.abs(go[name]).max(), 1e-12)
+    assert _wrel(g.forwardpass(g.p0, "train"), o.forwardpass(o.p0, "train")) < 1e-6
