@@ -32,6 +32,9 @@ CONFIGS = {
     7: dict(name="3 heads: 2 subunits softplus/softplus + history, 2^23 samples",
             dims=[25, 20, 15], df=[8, 6, 6], n_raw=1 << 23, distr="poisson", out="softplus", filt="softplus",
             subunits=2, history=True, dev=0.0, alpha=1.0, beta=0.01, step=0.01, iters=40),
+    8: dict(name="4 heads: 3 subunits softplus/softplus + history, 2^23 samples",
+            dims=[25, 20, 15], df=[8, 6, 6], n_raw=1 << 23, distr="poisson", out="softplus", filt="softplus",
+            subunits=3, history=True, dev=0.0, alpha=1.0, beta=0.01, step=0.01, iters=40),
     5: dict(name="config 5: LG dims [40,32,32] df [12,10,10] (1200 coefficients), 2^24 samples",
             dims=[40, 32, 32], df=[12, 10, 10], n_raw=1 << 24, distr="gaussian", out="none", filt="none",
             subunits=1, history=False, dev=0.0, alpha=1.0, beta=0.001, step=0.01, iters=30),
