@@ -1,10 +1,11 @@
 """Oracle: the `rfest.GLM` model object and its fit loop, on the CPU.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED against the
-reference itself for everything that is JAX in the reference (forward pass,
-autodiff gradient, Adam, `jax.random`): JAX cannot be installed in this image.
-It is pinned indirectly -- finite differences, `torch.autograd`,
-`torch.optim.Adam`, the reference's own recovery thresholds (tests/).
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Pinned to the reference's own code:
+`oracle/ref_glm.py` runs `rfest/GLM/_glm.py` + `rfest/loss.py` unmodified (through the
+test-only `jax` package of `oracle/_jaxshim/`, JAX itself cannot be installed here) and
+`tests/test_ref_pinning.py` holds this file to that run (<= 1e-10 relative in float64,
+float32 rounding in float32) and to the committed outputs `tests/golden/ref_glm_golden.npz`.
+Not pinnable without real JAX: `jax.random` draws and XLA's summation order.
 
 Restates, with NumPy only:
   rfest/GLM/_glm.py:103-170   nonlinearities (naive softplus + 1e-7, ...)
@@ -22,11 +23,13 @@ Restates, with NumPy only:
 Two arithmetic modes:
   dtype=np.float64  everything in double -- the reference's default dtype and
                     the "truth" the fp32 paths are measured against.
-  dtype=np.float32  stand-in for the reference's fp32 JAX path with
-                    `jax_enable_x64` on: arrays are float32, Python-float
-                    leaves (the intercepts) are weak-typed float64 scalars
-                    whose Adam state stays in float64 but which enter array
-                    arithmetic rounded to float32.
+  dtype=np.float32  the reference's fp32 path with `jax_enable_x64` on (set by
+                    `import rfest`): arrays are float32; Python-float intercept leaves
+                    are weak-typed, so iteration 0 runs entirely in float32, but their
+                    Adam state is float64 and from the first update on they are float64
+                    arrays -- `XS @ b + intercept` and the nonlinearities then promote
+                    to float64 until `forwardpass` casts the prediction back to float32
+                    (see `_scalar`).
 
 The autodiff gradient is restated in the order JAX's reverse mode evaluates
 it (cotangent / s * e for the softplus, etc.), which only matters at the ulp
@@ -400,8 +403,16 @@ class OracleGLM:
 
     # ---- forward / cost / gradient ---------------------------------------
     def _scalar(self, c):
-        """A weak-typed scalar entering array arithmetic: rounded to the array dtype."""
-        return self.dtype(np.asarray(c, dtype=np.float64).reshape(()))
+        """An intercept leaf entering array arithmetic, with JAX's promotion under
+        `jax_enable_x64` (= NumPy's NEP 50): a Python float (the initial 0.0 of
+        _glm.py:311,322) is weak and takes the array dtype; an array leaf keeps its own
+        dtype -- after the first Adam update the intercepts are float64 arrays, so in
+        float32 mode `XS @ b + intercept` and every nonlinearity after it run in float64
+        until `forwardpass` casts the prediction back (`.astype(self.dtype)`, :568-571).
+        Confirmed against the reference run through oracle/_jaxshim."""
+        if type(c) is float or type(c) is int:
+            return self.dtype(c)
+        return np.asarray(c).reshape(())[()]
 
     def _forward_parts(self, p, kind):
         icpt = p["intercept"]
@@ -451,14 +462,17 @@ class OracleGLM:
                 d_r = loss_mse_vjp(y, r)
             else:
                 d_r = loss_neglogli_vjp(y, r)
-            d_u = fnl_vjp(u, d_r, self.output_nonlinearity)
-            d_u = np.where(np.isnan(d_u) & (d_r == 0), self.dtype(0), d_u)
+            # cotangents take the dtype of the value they belong to (the transpose of a
+            # promotion is a cast back): u and the activations may be float64 in float32 mode
+            d_u = fnl_vjp(u, d_r.astype(u.dtype), self.output_nonlinearity)
+            d_u = np.where(np.isnan(d_u) & (d_r == 0), u.dtype.type(0), d_u)
 
             grads = {"intercept": {"global": np.sum(d_u)}}
             for name in self.X[kind]:
                 M = self.XS[kind][name] if name in self.S else self.X[kind][name]
-                d_a = fnl_vjp(acts[name], d_u, self.filter_nonlinearity[name])
-                grads[name] = (M.T @ d_a)[:, np.newaxis]
+                a = acts[name]
+                d_a = fnl_vjp(a, d_u.astype(a.dtype), self.filter_nonlinearity[name])
+                grads[name] = M.T @ d_a.astype(M.dtype)[:, np.newaxis]   # (p, n) @ (n, 1), as the transpose of XS @ b
                 grads["intercept"][name] = np.sum(d_a)
 
             if self._penalised(kind, True):
@@ -485,14 +499,20 @@ class OracleGLM:
         assert ("dev" in self.y) or ("dev" not in return_model), \
             "Cannot use dev set if dev set is not given."
 
-        # optimiser state: filter leaves in self.dtype, intercept leaves float64 (weak)
+        # optimiser state: filter leaves in self.dtype.  An intercept leaf keeps the type it
+        # arrives with: a Python float (random init, _glm.py:311,322) is a weak float64
+        # scalar -- its Adam state is float64 and after the first update it is a float64
+        # array; an array leaf (the (1,)-shaped intercepts of the mle init, :497) stays in
+        # its own dtype and shape.
         names = list(self.filter_names)
         x = {n: np.asarray(p0[n], dtype=self.dtype).copy() for n in names}
-        xi = {k: np.float64(np.asarray(v).reshape(())) for k, v in p0["intercept"].items()}
+        xi = {k: (float(v) if type(v) in (float, int) else np.asarray(v).copy())
+              for k, v in p0["intercept"].items()}
+        ti = {k: (np.float64 if type(c) is float else c.dtype.type) for k, c in xi.items()}
         m = {n: np.zeros_like(x[n]) for n in names}
         v = {n: np.zeros_like(x[n]) for n in names}
-        mi = {k: np.float64(0) for k in xi}
-        vi = {k: np.float64(0) for k in xi}
+        mi = {k: np.zeros_like(c, dtype=ti[k]) for k, c in xi.items()}
+        vi = {k: np.zeros_like(c, dtype=ti[k]) for k, c in xi.items()}
 
         def pack():
             p = {n: x[n].copy() for n in names}
@@ -521,8 +541,8 @@ class OracleGLM:
                 x[n], m[n], v[n] = adam_step(i, x[n], g[n].astype(self.dtype), m[n], v[n],
                                              lr, self.dtype)
             for k in xi:
-                xi[k], mi[k], vi[k] = adam_step(i, xi[k], np.float64(g["intercept"][k]),
-                                                mi[k], vi[k], lr, np.float64)
+                gk = np.asarray(g["intercept"][k], dtype=ti[k]).reshape(np.shape(xi[k]))
+                xi[k], mi[k], vi[k] = adam_step(i, xi[k], gk, mi[k], vi[k], lr, ti[k])
             params = pack()                                                 # post-update
             params_list.append(params)
 

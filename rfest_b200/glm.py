@@ -763,7 +763,7 @@ class GLM:
                     if np.all(-np.diff(c_tr[i - tolerance:i]) < atol):
                         i_stop, stop = i, "train_stop"
                         break
-                next_scan = executed
+                next_scan = max(next_scan, executed)       # never before min_iters + 1 (_glm.py:748)
         i = executed - 1 if i_stop is None else i_stop
         dm.fit_finish(i)                     # completes trace row i, keeps its predictions
         cost_train, cost_dev, metric_train, metric_dev = dm.fit_traces(i + 1)
