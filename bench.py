@@ -16,7 +16,14 @@ e2e      the same K iterations through the public API `GLM.fit(y=<pinned host ar
          region (the design XS stays resident, as it does in the reference after
          add_design_matrix).
 roofline train-sweep kernel only: algorithmic bytes 4 * n_local * (296 + 1) per launch over the
-         kernel's mean duration (CUDA events around each launch, `rfb_fit_run_timed`).
+         kernel's mean duration IN THE TIMED REGION: every CTA of the sweep folds %globaltimer into a
+         per-iteration (first entry, last exit) pair inside the replayed graph (`rfb_fit_sweep_times`).
+         `kernel_ms_eager` repeats the iterations eagerly with CUDA events around each kernel as a
+         cross-check.
+extras   (N=1 only, after the headline; `--no-extras` skips them) `other_configs`: BASELINE configs 2, 4, 5
+         and 1 timed the same way; `projection`: the one-time K1 (tcgen05 spatial GEMM + temporal step) on
+         device-resident frames; `setup_host`: `add_design_matrix(<host ndarray>)` wall clock through the
+         pinned ring against the serial round-1 path.
 """
 
 import argparse
@@ -47,6 +54,8 @@ def parse():
     ap.add_argument("--log2n", type=int, default=25, help="log2 of the number of raw samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-log2n", type=int, default=21)
+    ap.add_argument("--no-extras", action="store_true", help="headline only (no other configs / projection)")
+    ap.add_argument("--host-log2n", type=int, default=22, help="frames of the host-array projection timing")
     return ap.parse_args()
 
 
@@ -68,10 +77,21 @@ def cpu_arm(log2n_workload, log2n_sample, steps, warmup):
     m.filter_names = ["stimulus", "history"]
     m.filter_nonlinearity = {"stimulus": "none", "history": "none"}
     m.X["train"] = {"stimulus": None, "history": None}
-    m.XS["train"] = {"stimulus": rng.standard_normal((n, 288), dtype=np.float32) * 0.06,
-                     "history": rng.standard_normal((n, 8), dtype=np.float32) * 0.1}
+    # random rows are drawn for at most 2^21 samples and repeated beyond that (the arithmetic and the
+    # memory traffic per iteration do not depend on the values; drawing 10^10 normals would take minutes)
+    nb = min(n, 1 << 21)
+    blk_s = rng.standard_normal((nb, 288), dtype=np.float32) * 0.06
+    blk_h = rng.standard_normal((nb, 8), dtype=np.float32) * 0.1
+    blk_y = rng.poisson(0.3, nb).astype(np.float32)
+    if nb == n:
+        xs_s, xs_h, yy = blk_s, blk_h, blk_y
+    else:
+        xs_s, xs_h, yy = np.empty((n, 288), np.float32), np.empty((n, 8), np.float32), np.empty(n, np.float32)
+        for k0 in range(0, n, nb):
+            xs_s[k0:k0 + nb], xs_h[k0:k0 + nb], yy[k0:k0 + nb] = blk_s, blk_h, blk_y
+    m.XS["train"] = {"stimulus": xs_s, "history": xs_h}
     m.S = {"stimulus": None, "history": None}
-    m.y["train"] = rng.poisson(0.3, n).astype(np.float32)
+    m.y["train"] = yy
     m.alpha, m.beta = ALPHA, BETA
     m.burn_in = 0
     p0 = {"stimulus": (0.1 * np.random.default_rng(2046).standard_normal((288, 1))).astype(np.float32),
@@ -96,11 +116,29 @@ def cpu_arm(log2n_workload, log2n_sample, steps, warmup):
         limiter.restore_original_limits()
     its = steps / dt
     scaled = its * n / float(1 << log2n_workload)
+    full = log2n_sample >= log2n_workload
     return {"value": scaled, "unit": "iterations/s", "cores": cores, "kind": "port",
             "threads": blas_threads if blas_threads is not None else torch.get_num_threads(),
-            "sample": f"oracle fp32 NumPy restatement, XS injected, n=2^{log2n_sample} rows x 296 cols, "
-                      f"{steps} iterations in {dt:.2f} s = {its:.3f} it/s; linearly extrapolated to "
-                      f"n=2^{log2n_workload}"}
+            "extrapolated": not full, "sample_ms_per_step": 1e3 * dt / steps, "sample_log2n": log2n_sample,
+            "sample": f"oracle fp32 NumPy restatement (pinned to the reference's own _glm.py, see oracle/), XS "
+                      f"injected, n=2^{log2n_sample} rows x 296 cols, {steps} iterations in {dt:.2f} s = "
+                      f"{its:.3f} it/s" + ("; the full workload, nothing extrapolated" if full else
+                                           f"; LINEARLY EXTRAPOLATED to n=2^{log2n_workload}")}
+
+
+def reference_sample_log2n(log2n_workload, requested):
+    """Largest sample the reference arm can hold: the whole workload when the host has the memory for XS
+    (4 * n * 296 bytes) plus the loop's n-vectors, else the requested bounded sample."""
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        return requested
+    l2 = log2n_workload
+    while l2 > requested and (1 << l2) * (4.0 * 296 + 8.0 * 40) * 1.25 > avail:
+        l2 -= 1
+    return max(l2, requested)
 
 
 # --------------------------------------------------------------------------------------------
@@ -228,18 +266,23 @@ def gpu_arm(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     gpu_launches = eng.launch_count - launches0
+    sweep_in_graph = dm.fit_sweep_times("train", W, K)       # the timed iterations themselves
     # per-kernel timing of the same iterations launched eagerly with events around each kernel
     ms4 = dm.fit_run_timed(K)
     clocks = sampler.stop() if sampler else None
     dm.fit_finish(W + 2 * K - 1)
     traces = dm.fit_traces(W + 2 * K)
     dm.fit_end()
+    sweep_ms = float(np.mean(sweep_in_graph))
     if world > 1:
-        t = torch.tensor([ms, ms4[0]], device=f"cuda:{local_rank}", dtype=torch.float64)
+        t = torch.tensor([ms, sweep_ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        all_sweeps = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(all_sweeps, t)
+        rank_sweep_ms = [float(x[1]) for x in all_sweeps]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, sweep_ms = float(t[0]), float(t[1])
     else:
-        sweep_ms = float(ms4[0])
+        rank_sweep_ms = [sweep_ms]
 
     # ---- end to end through the public API, host buffers ---------------------------------------------
     y_host = torch.empty(n_local + burn, dtype=torch.float32).pin_memory()
@@ -260,6 +303,18 @@ def gpu_arm(args):
         t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
+    # variant that also brings the final predictions to the host (pinned buffer)
+    pred_host = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    model.fit(y=y_arg, num_iters=K, step_size=STEP_SIZE, beta=BETA, alpha=ALPHA, verbose=0, tolerance=0)
+    pred_host.copy_(model.y_pred["opt"]["train"].as_torch(), non_blocking=False)
+    eng.synchronize()
+    e2e_pred_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_pred_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_pred_s = float(t[0])
     P = 296
     h2d = (4 * n_local + 4 * P + 8 * 3 + 8 * K) / K
     d2h = (4 * 8 * K + K * (4 * P + 8 * 3)) / K      # traces + every iteration's parameters
@@ -305,20 +360,60 @@ def gpu_arm(args):
                 "d2h_bytes_per_step": d2h,
                 "what": "GLM.fit(y=pinned host array, num_iters=K) wall clock: H2D of y, graph capture, K "
                         "iterations, trailing forward pass, D2H of the loss/metric traces and all parameters; "
-                        "predictions stay on the device (as the reference's JAX arrays do) until read"},
+                        "predictions stay on the device (as the reference's JAX arrays do) until read. "
+                        "K iterations cost K + 1 sweeps (the reference's forward pass at the final parameters "
+                        "for metric_train[K-1] / y_pred), so e2e <= K / (K + 1) of `value`",
+                "with_predictions": {"value": K / e2e_pred_s, "unit": "iterations/s",
+                                     "d2h_bytes_per_step": d2h + 4.0 * n_local / K,
+                                     "what": "the same call followed by the D2H copy of y_pred['opt']['train'] "
+                                             "into pinned host memory"}},
         "gpu_launches": int(gpu_launches),
-        "kernel_ms": {"train_sweep": float(ms4[0]), "dev_sweep": float(ms4[1]),
-                      "reduce_allreduce": float(ms4[2]), "update": float(ms4[3])},
+        "kernel_ms": {"train_sweep": sweep_ms, "rest_of_step": ms / K - sweep_ms,
+                      "how": "train_sweep: in-graph %globaltimer stamps of the K timed iterations (max over "
+                             "ranks of the per-rank mean); rest_of_step: ms_per_step minus that"},
+        "kernel_ms_eager": {"train_sweep": float(ms4[0]), "dev_sweep": float(ms4[1]),
+                            "reduce_allreduce": float(ms4[2]), "update": float(ms4[3]),
+                            "how": "the same iterations relaunched eagerly with CUDA events around each kernel"},
+        "rank_sweep_ms": rank_sweep_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "frac_of_nominal_8000": achieved / 8000.0,
-                     "kernel": "rfb::sweep_staged_kernel<1,3,8,true,1>", "bytes_per_launch": alg_bytes},
+                     "kernel": "rfb::sweep_staged_kernel<1,3,8,true,1>", "bytes_per_launch": alg_bytes,
+                     "timed": "inside the timed region (in-graph stamps)"},
         "clocks": clocks,
         "loss_first_last": [float(traces[0][0]), float(traces[0][-1])],
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_arm(args.log2n, args.cpu_log2n, 60, 3)
+    if world == 1 and not args.no_extras:
+        # free the headline's 40 GB before the other configurations allocate theirs
+        del model, dm, stim, y_dev, y_rows, y_local
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs as bc
+
+        extras = {}
+        for cid, iters in ((2, 40), (4, 40), (5, 20), (1, 1000)):
+            try:
+                extras[f"config{cid}"] = bc.run(cid, iters=iters, quiet=True)
+            except Exception as exc:                      # an extra must not cost the headline
+                extras[f"config{cid}"] = {"error": repr(exc)}
+        out["other_configs"] = extras
+        proj = {}
+        for label, dims, df, l2n in (("config3_shape", DIMS, DF, 22), ("config5_shape", [40, 32, 32], [12, 10, 10], 20)):
+            try:
+                proj[label] = bc.projection(dims, df, l2n)
+            except Exception as exc:
+                proj[label] = {"error": repr(exc)}
+        out["projection"] = proj
+        try:
+            out["setup_host"] = bc.host_projection(DIMS, DF, args.host_log2n)
+        except Exception as exc:
+            out["setup_host"] = {"error": repr(exc)}
     if world > 1:
         dist.destroy_process_group()
     return out
@@ -331,10 +426,15 @@ def main():
         if rank != 0:
             return
         steps = max(args.steps, 1)
-        base = cpu_arm(args.log2n, args.cpu_log2n, min(steps, 60), min(max(args.warmup, 1), 5))
+        sample = reference_sample_log2n(args.log2n, args.cpu_log2n) if os.environ.get(
+            "RFB_REFERENCE_FULL", "1") != "0" else args.cpu_log2n
+        big = sample > 22        # >= 0.3 s per iteration: keep the whole run within a few minutes
+        base = cpu_arm(args.log2n, sample, min(steps, 20 if big else 60), min(max(args.warmup, 1), 2 if big else 5))
         out = {
             "impl": "reference",
-            "metric": "spline-GLM fit iterations/s at the 2^%d x 288 design" % args.log2n,
+            "metric": "spline-GLM fit iterations/s at the 2^%d x 288 design%s" % (
+                args.log2n, " (CPU port, extrapolated from a 2^%d-row sample)" % sample if base["extrapolated"] else
+                " (CPU port of the reference loop, measured at the full size)"),
             "value": base["value"], "unit": "iterations/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",

@@ -149,6 +149,13 @@ int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out, int col0,
                       int64_t n_raw_total, int n_pix, int64_t first_t, int nlag, int shift,
                       const float* St, int df_t, const float* Sxy, int n_q);
 
+/* Bytes rfb_block_project moved host -> device in its last call on this engine (0 for device input). */
+int rfb_engine_last_project_h2d_bytes(rfb_engine* e, double* out);
+/* out[n_rows x k] = block @ B, B [n_cols x k] row-major, both host arrays: what user code writes as
+ * `model.XS[kind][name] @ b` (rfest/GLM/_glm.py:562,1127) -- computed on the device, the block is not
+ * copied to the host. */
+int rfb_block_matmul(rfb_block* b, const float* B, int k, float* out);
+
 /* ---- model: filters, data, parameters --------------------------------------------------- */
 /* GLM(distr, output_nonlinearity), rfest/GLM/_glm.py:25 */
 int rfb_model_create(rfb_engine* e, int distr, int output_nl, rfb_model** out);
@@ -228,6 +235,11 @@ int rfb_fit_run(rfb_model* m, int n_iters);
  * around each kernel: ms4 = mean milliseconds of {train sweep, dev sweep, reduction + all-reduce,
  * update}.  For bench.py's per-kernel roofline. */
 int rfb_fit_run_timed(rfb_model* m, int n_iters, double* ms4);
+/* Duration (ms) of the train / dev sweep kernel of iterations [i0, i0 + n), measured INSIDE the
+ * replayed graph: every CTA of a sweep folds %globaltimer into a per-iteration (first entry, last exit)
+ * pair, so these are the kernel times of the very iterations rfb_fit_run executed (no events, no
+ * eager relaunch).  NaN where no sweep ran. */
+int rfb_fit_sweep_times(rfb_model* m, int kind, int i0, int n, double* ms_out);
 /* Number of iterations executed so far. */
 int rfb_fit_iterations(rfb_model* m, int* out);
 /* Make iteration `i_last` (< executed) the final one: its parameters become current, the

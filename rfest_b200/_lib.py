@@ -57,6 +57,8 @@ SIGNATURES = {
     "rfb_block_write": (_i, [_p, _i64, _i64, _p, _i]),
     "rfb_block_project": (_i, [_p, _i64, _i64, _i, _p, _i, _i64, _i64, _i64, _i, _i64, _i, _i,
                                 _p, _i, _p, _i]),
+    "rfb_engine_last_project_h2d_bytes": (_i, [_p, _dp]),
+    "rfb_block_matmul": (_i, [_p, _p, _i, _p]),
     "rfb_model_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
     "rfb_model_destroy": (_i, [_p]),
     "rfb_model_clear_filters": (_i, [_p]),
@@ -73,6 +75,7 @@ SIGNATURES = {
     "rfb_fit_begin": (_i, [_p, _i, _p, _d, _d, _i]),
     "rfb_fit_run": (_i, [_p, _i]),
     "rfb_fit_run_timed": (_i, [_p, _i, _dp]),
+    "rfb_fit_sweep_times": (_i, [_p, _i, _i, _i, _dp]),
     "rfb_fit_iterations": (_i, [_p, _ip]),
     "rfb_fit_finish": (_i, [_p, _i]),
     "rfb_fit_traces": (_i, [_p, _i, _p, _p, _p, _p]),

@@ -55,7 +55,24 @@ struct SweepArgs {
   int sub_head[4];                  // head index (accumulator layout) of every subunit
   int sub_extra_head;               // head over the remaining (<= 8) chunks, -1: none
   int layout_heads;                 // heads in the accumulator layout (the plan's template head count)
+  // in-graph timing of the fit loop: when `stamp` is set every CTA folds %globaltimer into
+  // stamp[2 * (*stamp_it)] (min at entry) and stamp[2 * (*stamp_it) + 1] (max at exit)
+  unsigned long long* stamp;
+  const int* stamp_it;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void sweep_stamp(const SweepArgs& a, int end) {
+  if (a.stamp != nullptr && threadIdx.x == 0) {
+    unsigned long long* s = a.stamp + 2 * (size_t)(*a.stamp_it) + end;
+    if (end) atomicMax(s, global_ns());
+    else atomicMin(s, global_ns());
+  }
+}
 
 // One-shot exchange over NVLink peer memory (multi-GPU): every rank owns a buffer
 //   [flags: 2 parities x kMaxRanks uint64][data: 2 parities x world x cap doubles]

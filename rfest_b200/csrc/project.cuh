@@ -267,6 +267,44 @@ __global__ void __launch_bounds__(128) temporal_project_const_kernel(const Tempo
   }
 }
 
+// ---- block @ matrix: out[r, j] = sum_c X[r, c] * B[c, j] for K <= 8 columns of B at a time ------------------
+// (`model.XS[kind][name] @ b` of user code, rfest/GLM/_glm.py:562,1127: one warp per row, float4 loads,
+// B through the read-only cache; HBM-bound: the block is read once per 8 columns of B)
+template <int K>
+__global__ void __launch_bounds__(256)
+block_matmul_kernel(const float* __restrict__ X, long long n_rows, int n_cols, long long ld,
+                    const float* __restrict__ B, int ldb, int j0, int kw, float* __restrict__ out, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nch = (n_cols + 3) / 4;                       // rows are padded to a multiple of 4 floats
+  for (long long r = warp; r < n_rows; r += n_warps) {
+    const float4* row = reinterpret_cast<const float4*>(X + r * ld);
+    float acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = 0.f;
+    for (int c4 = lane; c4 < nch; c4 += 32) {
+      const float4 x = __ldg(row + c4);
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c4 * 4 + u;
+        if (c < n_cols) {
+#pragma unroll
+          for (int j = 0; j < K; ++j)
+            if (j < kw) acc[j] = fmaf(xs[u], __ldg(B + (size_t)c * ldb + j0 + j), acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      float v = acc[j];
+      for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (lane == 0 && j < kw) out[r * ldo + j0 + j] = v;
+    }
+  }
+}
+
 // sum y, sum y^2 in fp64 (constants of the metrics, rfest/metrics.py:8-12)
 __global__ void __launch_bounds__(256) y_moments_kernel(const float* y, long long n, double* out2) {
   __shared__ double s0[8], s1[8];

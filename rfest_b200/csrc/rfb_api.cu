@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gram.cuh"
@@ -113,6 +114,18 @@ struct rfb_engine {
   void* comm = nullptr;
   int rank = 0, world = 1;
   Scratch stage, zbuf, stbuf, sxybuf, small, bsplit;
+  // host -> device staging ring of rfb_block_project: kRingSlots pinned bounce buffers + device slabs on a copy
+  // stream, so the host memcpy of slab i+1, the DMA of slab i and the projection kernels of slab i-1 overlap
+  static constexpr int kRingSlots = 3;
+  cudaStream_t copy_stream = nullptr;
+  void* ring_pinned[kRingSlots] = {};
+  void* ring_dev[kRingSlots] = {};
+  size_t ring_bytes = 0;
+  cudaEvent_t ring_copied[kRingSlots] = {}, ring_consumed[kRingSlots] = {};
+  int h2d_threads = 4;    // host threads filling a pinned slot from pageable memory
+  int h2d_overlap = 1;    // 0: the round-1 path (one staging buffer, synchronous per slab) for comparison
+  double last_project_h2d_bytes = 0.0;
+  int project_slab_rows = 0;   // rows per projection slab (0: sized from the frame size); tests shrink it
   int project_tc = 1;     // spatial projection on tensor cores (tcgen05, 3xTF32) when the shape allows
   // one-shot NVLink exchange (multi-GPU): local buffer, peers' mappings, device counters
   int use_xchg = 1;
@@ -247,6 +260,9 @@ struct Fit {
   double* fin = nullptr;  // [NE + kNumScalars]: train entries, then dev scalars
   UpdateArgs ua{};
   bool finished = false;
+  // %globaltimer stamps of the sweeps, written inside the replayed graph: [2 kinds][max_iters + 1][start, end]
+  unsigned long long* stamps = nullptr;
+  bool stamp_now = false;       // set while enqueue_iteration builds / launches an iteration
 };
 
 struct rfb_model {
@@ -708,6 +724,10 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   a.sub_slot = p.sub.slot;
   for (int k = 0; k < kSubMaxK; ++k) a.sub_head[k] = p.sub.heads[k];
   a.sub_extra_head = p.sub.extra_head;
+  if (m->fit.stamp_now && m->fit.stamps && kind <= RFB_KIND_DEV) {
+    a.stamp = m->fit.stamps + (size_t)kind * 2 * ((size_t)m->fit.max_iters + 1);
+    a.stamp_it = m->fit.it;
+  }
   if (sb.sub) {
     fn<<<sb.grid, sb.threads, sb.smem, e->stream>>>(a);
   } else if (p.generic) {
@@ -809,6 +829,8 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   if (const char* v = getenv("RFB_SWEEP_SUB")) e->sweep_sub = atoi(v);
   if (const char* v = getenv("RFB_PROJECT_TC")) e->project_tc = atoi(v);
   if (const char* v = getenv("RFB_XCHG")) e->use_xchg = atoi(v);
+  if (const char* v = getenv("RFB_H2D_THREADS")) e->h2d_threads = std::max(1, atoi(v));
+  if (const char* v = getenv("RFB_H2D_OVERLAP")) e->h2d_overlap = atoi(v);
   *out = e;
   return RFB_OK;
 }
@@ -823,6 +845,9 @@ extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) 
   else if (k == "sweep_sub") e->sweep_sub = value;
   else if (k == "project_tc") e->project_tc = value;
   else if (k == "xchg") e->use_xchg = value;
+  else if (k == "h2d_threads") e->h2d_threads = std::max(1, value);
+  else if (k == "h2d_overlap") e->h2d_overlap = value;
+  else if (k == "project_slab_rows") e->project_slab_rows = std::max(0, value);
   else return fail(RFB_ERR_INVALID, "unknown option '%s'", key);
   return RFB_OK;
 }
@@ -833,6 +858,13 @@ extern "C" int rfb_engine_destroy(rfb_engine* e) {
   cudaStreamSynchronize(e->stream);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (Scratch* s : {&e->stage, &e->zbuf, &e->stbuf, &e->sxybuf, &e->small, &e->bsplit}) cudaFree(s->p);
+  for (int k = 0; k < rfb_engine::kRingSlots; ++k) {
+    if (e->ring_pinned[k]) cudaFreeHost(e->ring_pinned[k]);
+    if (e->ring_dev[k]) cudaFree(e->ring_dev[k]);
+    if (e->ring_copied[k]) cudaEventDestroy(e->ring_copied[k]);
+    if (e->ring_consumed[k]) cudaEventDestroy(e->ring_consumed[k]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaStreamDestroy(e->stream);
   delete e;
   return RFB_OK;
@@ -1190,17 +1222,90 @@ static void launch_temporal(const TemporalArgs& a, cudaStream_t s, bool use_cons
   temporal_project_kernel<DFT, TT><<<(unsigned)blocks, threads, 0, s>>>(a);
 }
 
+extern "C" int rfb_block_matmul(rfb_block* b, const float* B, int k, float* out) {
+  if (!b || !B || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (k < 1) return fail(RFB_ERR_INVALID, "k must be >= 1");
+  if (b->n_rows == 0) return RFB_OK;
+  rfb_engine* e = b->e;
+  TRY(use_device(e));
+  float *d_B = nullptr, *d_out = nullptr;
+  CU(cudaMalloc(&d_B, sizeof(float) * (size_t)b->n_cols * k));
+  if (cudaMalloc(&d_out, sizeof(float) * (size_t)b->n_rows * k) != cudaSuccess) {
+    cudaFree(d_B);
+    return fail(RFB_ERR_CUDA, "out of device memory for a %lld x %d product", (long long)b->n_rows, k);
+  }
+  cudaMemcpyAsync(d_B, B, sizeof(float) * (size_t)b->n_cols * k, cudaMemcpyHostToDevice, e->stream);
+  const unsigned grid = (unsigned)std::min<long long>((b->n_rows + 7) / 8, (long long)e->num_sms * 8);
+  for (int j0 = 0; j0 < k; j0 += 8) {
+    block_matmul_kernel<8><<<grid, 256, 0, e->stream>>>(b->d, b->n_rows, b->n_cols, b->ld, d_B, k, j0,
+                                                         std::min(8, k - j0), d_out, k);
+    e->launches++;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess)
+    ce = cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)b->n_rows * k, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaFree(d_B);
+  cudaFree(d_out);
+  if (ce != cudaSuccess) return fail(RFB_ERR_CUDA, "block matmul: %s", cudaGetErrorString(ce));
+  return RFB_OK;
+}
+
+// Host memory -> pinned slot with a few threads (one memcpy thread moves ~10 GB/s, a PCIe 5 x16 link ~55 GB/s).
+static void parallel_memcpy(void* dst, const void* src, size_t bytes, int threads) {
+  threads = (int)std::min<size_t>((size_t)std::max(threads, 1), std::max<size_t>(bytes >> 22, 1));
+  if (threads <= 1) { memcpy(dst, src, bytes); return; }
+  const size_t per = ((bytes / threads) + 4095) & ~(size_t)4095;
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) {
+    const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+    if (hi > lo) pool.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+  }
+  memcpy(dst, src, std::min(bytes, per));
+  for (auto& th : pool) th.join();
+}
+
+static int ring_reserve(rfb_engine* e, size_t bytes, bool need_pinned) {
+  if (!e->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < rfb_engine::kRingSlots; ++k) {
+      CU(cudaEventCreateWithFlags(&e->ring_copied[k], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->ring_consumed[k], cudaEventDisableTiming));
+    }
+  }
+  if (e->ring_bytes < bytes) {
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->copy_stream));
+    for (int k = 0; k < rfb_engine::kRingSlots; ++k) {
+      if (e->ring_pinned[k]) { cudaFreeHost(e->ring_pinned[k]); e->ring_pinned[k] = nullptr; }
+      if (e->ring_dev[k]) { cudaFree(e->ring_dev[k]); e->ring_dev[k] = nullptr; }
+    }
+    e->ring_bytes = 0;
+    for (int k = 0; k < rfb_engine::kRingSlots; ++k) CU(cudaMalloc(&e->ring_dev[k], bytes));
+    e->ring_bytes = bytes;
+  }
+  if (need_pinned)
+    for (int k = 0; k < rfb_engine::kRingSlots; ++k)
+      if (!e->ring_pinned[k]) CU(cudaHostAlloc(&e->ring_pinned[k], e->ring_bytes, cudaHostAllocDefault));
+  return RFB_OK;
+}
+
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return attr.type == cudaMemoryTypeHost;
+}
+
 extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out, int col0,
                                  const float* stim, int on_device, int64_t src0, int64_t n_src,
                                  int64_t n_raw_total, int n_pix, int64_t first_t, int nlag, int shift,
                                  const float* St, int df_t, const float* Sxy, int n_q) {
   if (!dst || !stim || !St) return fail(RFB_ERR_INVALID, "NULL argument");
   if (nlag < 1 || df_t < 1 || n_pix < 1 || n_q < 1) return fail(RFB_ERR_INVALID, "bad dims");
-  if (df_t > 16) return fail(RFB_ERR_UNSUPPORTED, "df of the time axis > 16 (%d)", df_t);
   if (!Sxy && (n_pix != 1 || n_q != 1)) return fail(RFB_ERR_INVALID, "Sxy is NULL but n_pix/n_q != 1");
   if (dst_row0 < 0 || n_out < 0 || dst_row0 + n_out > dst->n_rows)
     return fail(RFB_ERR_INVALID, "destination rows out of bounds");
-  if (col0 < 0 || col0 + df_t * n_q > dst->n_cols) return fail(RFB_ERR_INVALID, "destination columns out of bounds");
+  if (col0 < 0 || (int64_t)col0 + (int64_t)df_t * n_q > dst->n_cols) return fail(RFB_ERR_INVALID, "destination columns out of bounds");
   if (n_src < 0 || src0 < 0 || src0 + n_src > n_raw_total) return fail(RFB_ERR_INVALID, "bad source range");
   if (n_out == 0) return RFB_OK;
   rfb_engine* e = dst->e;
@@ -1218,21 +1323,33 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
                   (long long)lo, (long long)hi, (long long)src0, (long long)(src0 + n_src));
   }
 
-  const int DFT = df_t <= 1 ? 1 : df_t <= 2 ? 2 : df_t <= 4 ? 4 : df_t <= 8 ? 8 : df_t <= 12 ? 12 : 16;
-  {
-    std::vector<float> stp((size_t)nlag * DFT, 0.f);
+  // The temporal kernels hold up to 16 basis columns per thread; a wider time basis (a filter without a
+  // spline basis hands over St = I[nlag], a spline with df[0] > 16) is applied in groups of <= 16 columns,
+  // each group writing its own column range of the block.
+  struct Group { int d0, dw, DFT; size_t off; };
+  std::vector<Group> groups;
+  std::vector<float> stp;                                   // all groups' [nlag x DFT] padded bases, back to back
+  for (int d0 = 0; d0 < df_t; d0 += 16) {
+    const int dw = std::min(16, df_t - d0);
+    const int DFT = dw <= 1 ? 1 : dw <= 2 ? 2 : dw <= 4 ? 4 : dw <= 8 ? 8 : dw <= 12 ? 12 : 16;
+    groups.push_back(Group{d0, dw, DFT, stp.size()});
+    stp.resize(stp.size() + (size_t)nlag * DFT, 0.f);
     for (int i = 0; i < nlag; ++i)
-      for (int d = 0; d < df_t; ++d) stp[(size_t)i * DFT + d] = St[(size_t)i * df_t + d];
-    TRY(scratch_reserve(e, e->stbuf, sizeof(float) * stp.size()));
-    CU(cudaMemcpyAsync(e->stbuf.p, stp.data(), sizeof(float) * stp.size(), cudaMemcpyHostToDevice, e->stream));
-    if (nlag <= kTempMaxLag) {   // zero-padded copy in constant memory for the fast temporal kernel
-      std::vector<float> cst((size_t)kTempMaxLag * 16, 0.f);
-      std::copy(stp.begin(), stp.end(), cst.begin());
-      CU(cudaMemcpyToSymbolAsync(c_st, cst.data(), sizeof(float) * cst.size(), 0, cudaMemcpyHostToDevice, e->stream));
-    }
-    CU(cudaStreamSynchronize(e->stream));
+      for (int d = 0; d < dw; ++d) stp[groups.back().off + (size_t)i * DFT + d] = St[(size_t)i * df_t + d0 + d];
   }
   const bool temporal_const = nlag <= kTempMaxLag && e->project_tc != 2;
+  std::vector<float> cst((size_t)kTempMaxLag * 16, 0.f);
+  auto upload_const = [&](const Group& g) -> int {          // zero-padded copy in constant memory (stream ordered)
+    std::fill(cst.begin(), cst.end(), 0.f);
+    std::copy(stp.begin() + g.off, stp.begin() + g.off + (size_t)nlag * g.DFT, cst.begin());
+    CU(cudaMemcpyToSymbolAsync(c_st, cst.data(), sizeof(float) * cst.size(), 0, cudaMemcpyHostToDevice, e->stream));
+    return RFB_OK;
+  };
+  TRY(scratch_reserve(e, e->stbuf, sizeof(float) * stp.size()));
+  CU(cudaMemcpyAsync(e->stbuf.p, stp.data(), sizeof(float) * stp.size(), cudaMemcpyHostToDevice, e->stream));
+  if (temporal_const && groups.size() == 1) TRY(upload_const(groups[0]));
+  CU(cudaStreamSynchronize(e->stream));
+
   TcPlan tcp;
   TRY(tc_prepare(e, Sxy, n_pix, n_q, &tcp));
   const float* d_sxy = nullptr;
@@ -1242,27 +1359,52 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
     d_sxy = (const float*)e->sxybuf.p;
   }
 
-  // rows per slab: host input is staged through <= 256 MB; device input only needs the Z scratch (<= 1 GB)
-  int64_t chunk = on_device ? (int64_t)(256u << 20) / n_q : (int64_t)(64u << 20) / n_pix;
+  // rows per slab.  Device input only needs the Z scratch (<= 1 GB).  Host input goes through the ring:
+  // slabs of <= 64 MB (<= 256 MB on the synchronous comparison path).
+  const bool ring = !on_device && e->h2d_overlap != 0;
+  int64_t chunk = on_device ? (int64_t)(256u << 20) / n_q : (int64_t)((ring ? 16u : 64u) << 20) / n_pix;
   chunk = std::min<int64_t>(std::max<int64_t>(chunk, 4096), on_device ? (1 << 23) : (1 << 20));
-  for (int64_t k0 = 0; k0 < n_out; k0 += chunk) {
+  if (e->project_slab_rows > 0) chunk = e->project_slab_rows;
+  const bool src_pinned = ring && is_pinned_host(stim);
+  if (ring) TRY(ring_reserve(e, sizeof(float) * (size_t)(chunk + nlag) * n_pix, !src_pinned));
+  e->last_project_h2d_bytes = 0.0;
+  int64_t slab = 0;
+  for (int64_t k0 = 0; k0 < n_out; k0 += chunk, ++slab) {
     const int64_t kc = std::min<int64_t>(chunk, n_out - k0);
     int64_t lo = first_t + k0 - front, hi = first_t + k0 + kc - 1 + nlag - 1 - front;
     lo = std::max<int64_t>(lo, 0);
     hi = std::min<int64_t>(hi, n_raw_total - 1);
     const int64_t nz = hi >= lo ? hi - lo + 1 : 0;
+    const int slot = (int)(slab % rfb_engine::kRingSlots);
 
     const float* d_z = nullptr;
     int ldz = n_q;
     if (nz > 0) {
       const float* d_stim = nullptr;
+      const float* h_src = stim + (lo - src0) * (int64_t)n_pix;
+      const size_t bytes = sizeof(float) * (size_t)nz * n_pix;
       if (on_device) {
-        d_stim = stim + (lo - src0) * (int64_t)n_pix;
+        d_stim = h_src;
+      } else if (ring) {
+        const void* from = h_src;
+        if (!src_pinned) {
+          // the pinned slot is free once the DMA that last read it has finished
+          if (slab >= rfb_engine::kRingSlots) CU(cudaEventSynchronize(e->ring_copied[slot]));
+          parallel_memcpy(e->ring_pinned[slot], h_src, bytes, e->h2d_threads);
+          from = e->ring_pinned[slot];
+        }
+        // the device slab is free once the kernels of the slab that last used it have run
+        if (slab >= rfb_engine::kRingSlots) CU(cudaStreamWaitEvent(e->copy_stream, e->ring_consumed[slot], 0));
+        CU(cudaMemcpyAsync(e->ring_dev[slot], from, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        CU(cudaEventRecord(e->ring_copied[slot], e->copy_stream));
+        CU(cudaStreamWaitEvent(e->stream, e->ring_copied[slot], 0));
+        d_stim = (const float*)e->ring_dev[slot];
+        e->last_project_h2d_bytes += (double)bytes;
       } else {
-        TRY(scratch_reserve(e, e->stage, sizeof(float) * (size_t)nz * n_pix));
-        CU(cudaMemcpyAsync(e->stage.p, stim + (lo - src0) * (int64_t)n_pix, sizeof(float) * (size_t)nz * n_pix,
-                           cudaMemcpyHostToDevice, e->stream));
+        TRY(scratch_reserve(e, e->stage, bytes));
+        CU(cudaMemcpyAsync(e->stage.p, h_src, bytes, cudaMemcpyHostToDevice, e->stream));
         d_stim = (const float*)e->stage.p;
+        e->last_project_h2d_bytes += (double)bytes;
       }
       if (Sxy) {
         TRY(scratch_reserve(e, e->zbuf, sizeof(float) * (size_t)nz * n_q));
@@ -1278,36 +1420,46 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
         ldz = 1;
       }
     }
-    TemporalArgs a{};
-    a.Z = d_z;
-    a.z_src0 = lo;
-    a.n_z = nz;
-    a.ldz = ldz;
-    a.n_raw_total = n_raw_total;
-    a.out = dst->d;
-    a.out_ld = dst->ld;
-    a.out_row0 = dst_row0 + k0;
-    a.n_out = kc;
-    a.col0 = col0;
-    a.first_t = first_t + k0;
-    a.front = front;
-    a.nlag = nlag;
-    a.df_t = df_t;
-    a.n_q = n_q;
-    a.St = (const float*)e->stbuf.p;
-    switch (DFT) {
-      case 1: launch_temporal<1>(a, e->stream, temporal_const); break;
-      case 2: launch_temporal<2>(a, e->stream, temporal_const); break;
-      case 4: launch_temporal<4>(a, e->stream, temporal_const); break;
-      case 8: launch_temporal<8>(a, e->stream, temporal_const); break;
-      case 12: launch_temporal<12>(a, e->stream, temporal_const); break;
-      default: launch_temporal<16>(a, e->stream, temporal_const); break;
+    for (const Group& g : groups) {
+      if (temporal_const && groups.size() > 1) TRY(upload_const(g));
+      TemporalArgs a{};
+      a.Z = d_z;
+      a.z_src0 = lo;
+      a.n_z = nz;
+      a.ldz = ldz;
+      a.n_raw_total = n_raw_total;
+      a.out = dst->d;
+      a.out_ld = dst->ld;
+      a.out_row0 = dst_row0 + k0;
+      a.n_out = kc;
+      a.col0 = col0 + g.d0 * n_q;
+      a.first_t = first_t + k0;
+      a.front = front;
+      a.nlag = nlag;
+      a.df_t = g.dw;
+      a.n_q = n_q;
+      a.St = (const float*)e->stbuf.p + g.off;
+      switch (g.DFT) {
+        case 1: launch_temporal<1>(a, e->stream, temporal_const); break;
+        case 2: launch_temporal<2>(a, e->stream, temporal_const); break;
+        case 4: launch_temporal<4>(a, e->stream, temporal_const); break;
+        case 8: launch_temporal<8>(a, e->stream, temporal_const); break;
+        case 12: launch_temporal<12>(a, e->stream, temporal_const); break;
+        default: launch_temporal<16>(a, e->stream, temporal_const); break;
+      }
+      e->launches++;
+      CU(cudaGetLastError());
     }
-    e->launches++;
-    CU(cudaGetLastError());
-    if (!on_device) CU(cudaStreamSynchronize(e->stream));  // the staging buffer is reused
+    if (ring && nz > 0) CU(cudaEventRecord(e->ring_consumed[slot], e->stream));
+    if (!on_device && !ring) CU(cudaStreamSynchronize(e->stream));  // the single staging buffer is reused
   }
   CU(cudaStreamSynchronize(e->stream));
+  return RFB_OK;
+}
+
+extern "C" int rfb_engine_last_project_h2d_bytes(rfb_engine* e, double* out) {
+  if (!e || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  *out = e->last_project_h2d_bytes;
   return RFB_OK;
 }
 
@@ -1845,7 +1997,7 @@ static int fit_release(rfb_model* m) {
   if (f.graph) cudaGraphDestroy(f.graph);
   cudaFree(f.step); cudaFree(f.cost_train); cudaFree(f.cost_dev); cudaFree(f.metric_train);
   cudaFree(f.metric_dev); cudaFree(f.ring_b); cudaFree(f.ring_ic); cudaFree(f.it);
-  cudaFree(f.m); cudaFree(f.v); cudaFree(f.mi); cudaFree(f.vi); cudaFree(f.fin);
+  cudaFree(f.m); cudaFree(f.v); cudaFree(f.mi); cudaFree(f.vi); cudaFree(f.fin); cudaFree(f.stamps);
   f = Fit();
   return RFB_OK;
 }
@@ -1869,13 +2021,19 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   const bool softmax = m->out_nl == RFB_NL_SOFTMAX;
   if (ev) CU(cudaEventRecord(ev[0], e->stream));
   if (softmax) TRY(softmax_prepare(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only));
-  TRY(launch_sweep(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only, r_train, -1,
-                   softmax ? m->sm_f[RFB_KIND_TRAIN] : nullptr));
+  f.stamp_now = true;
+  int rc_sweep = launch_sweep(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only, r_train, -1,
+                              softmax ? m->sm_f[RFB_KIND_TRAIN] : nullptr);
+  f.stamp_now = false;
+  TRY(rc_sweep);
   if (ev) CU(cudaEventRecord(ev[1], e->stream));
   if (f.has_dev) {
     if (softmax) TRY(softmax_prepare(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false));
-    TRY(launch_sweep(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false, r_dev, -1,
-                     softmax ? m->sm_f[RFB_KIND_DEV] : nullptr));
+    f.stamp_now = true;
+    rc_sweep = launch_sweep(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false, r_dev, -1,
+                            softmax ? m->sm_f[RFB_KIND_DEV] : nullptr);
+    f.stamp_now = false;
+    TRY(rc_sweep);
   }
   if (ev) CU(cudaEventRecord(ev[2], e->stream));
   const int tail = p.Ht * p.ctot;
@@ -1957,6 +2115,14 @@ extern "C" int rfb_fit_begin(rfb_model* m, int max_iters, const double* step_siz
   CU(cudaMalloc(&f.mi, sizeof(double) * nk));
   CU(cudaMalloc(&f.vi, sizeof(double) * nk));
   CU(cudaMalloc(&f.fin, sizeof(double) * ((size_t)p.NE + kNumScalars)));
+  {
+    const size_t ns = 2 * 2 * (nd + 1);
+    std::vector<unsigned long long> init(ns);
+    for (size_t k = 0; k < ns; ++k) init[k] = (k & 1) ? 0ull : ~0ull;       // start: min-folded, end: max-folded
+    CU(cudaMalloc(&f.stamps, sizeof(unsigned long long) * ns));
+    CU(cudaMemcpyAsync(f.stamps, init.data(), sizeof(unsigned long long) * ns, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
   CU(cudaMemcpyAsync(f.step, step_sizes, sizeof(double) * nd, cudaMemcpyHostToDevice, e->stream));
   CU(cudaMemsetAsync(f.it, 0, sizeof(int), e->stream));
   CU(cudaMemsetAsync(f.m, 0, sizeof(float) * np, e->stream));
@@ -2068,6 +2234,24 @@ extern "C" int rfb_fit_run_timed(rfb_model* m, int n_iters, double* ms4) {
   }
   for (auto& x : ev) cudaEventDestroy(x);
   return rc;
+}
+
+extern "C" int rfb_fit_sweep_times(rfb_model* m, int kind, int i0, int n, double* ms_out) {
+  if (!m || !ms_out) return fail(RFB_ERR_INVALID, "NULL argument");
+  if (kind != RFB_KIND_TRAIN && kind != RFB_KIND_DEV) return fail(RFB_ERR_INVALID, "bad kind");
+  Fit& f = m->fit;
+  if (!f.active || !f.stamps) return fail(RFB_ERR_STATE, "no fit in progress");
+  if (i0 < 0 || n < 0 || i0 + n > f.executed) return fail(RFB_ERR_INVALID, "iterations [%d, %d) were not all executed (%d were)", i0, i0 + n, f.executed);
+  TRY(use_device(m->e));
+  std::vector<unsigned long long> st(2 * (size_t)n);
+  CU(cudaStreamSynchronize(m->e->stream));
+  CU(cudaMemcpy(st.data(), f.stamps + (size_t)kind * 2 * ((size_t)f.max_iters + 1) + 2 * (size_t)i0,
+                sizeof(unsigned long long) * st.size(), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n; ++k) {
+    const unsigned long long a = st[2 * k], b = st[2 * k + 1];
+    ms_out[k] = (a == ~0ull || b < a) ? std::nan("") : (double)(b - a) * 1e-6;
+  }
+  return RFB_OK;
 }
 
 extern "C" int rfb_fit_iterations(rfb_model* m, int* out) {

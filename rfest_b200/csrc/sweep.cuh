@@ -331,6 +331,7 @@ __device__ __forceinline__ void cta_reduce(const SweepArgs& a, int ctot, int NE)
 // ================================================================================================
 template <int H, int NCH, int RB, bool BWD>
 __global__ void __launch_bounds__(kSweepThreads) sweep_direct_kernel(const __grid_constant__ SweepArgs a) {
+  sweep_stamp(a, 0);
   static_assert(RB >= 1 && RB <= 32 && (RB & (RB - 1)) == 0, "RB must be a power of two");
   const int lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_direct_kernel(const __gri
   }
   flush_partials<H, NCH, RB, BWD>(my_acc, ctot, lane, cvalid, g, sc);
   cta_reduce<H, NCH, BWD>(a, ctot, NE);
+  sweep_stamp(a, 1);
 }
 
 // ================================================================================================
@@ -489,6 +491,7 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32
 template <int H, int NCH, int RB, bool BWD, int SPEC>
 __global__ void __launch_bounds__(kSweepThreads, sweep_min_blocks(H, NCH, true))
 sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
+  sweep_stamp(a, 0);
   static_assert(RB >= 1 && RB <= 8 && (RB & (RB - 1)) == 0, "RB must be 1, 2, 4 or 8");
   extern __shared__ __align__(128) unsigned char sweep_smem[];
   const int lane = threadIdx.x & 31;
@@ -779,6 +782,7 @@ sweep_staged_kernel(const __grid_constant__ SweepArgs a) {
   flush_partials<H, NCH, RBS, BWD>(my_acc, ctot, lane, cvalid, g, sc);
   if constexpr (H > 1) flush_head_scalar<H, RBS>(my_acc, ctot, lane, sc_head);
   cta_reduce<H, NCH, BWD>(a, ctot, NE);
+  sweep_stamp(a, 1);
 }
 
 // ================================================================================================
@@ -793,6 +797,7 @@ constexpr int kGenHeads = kMaxHeads;
 
 template <bool BWD>
 __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __grid_constant__ SweepArgs a, int H) {
+  sweep_stamp(a, 0);
   const int lane = threadIdx.x & 31;
   const int wpc = blockDim.x >> 5;
   const long long gw = (long long)blockIdx.x * wpc + (threadIdx.x >> 5);
@@ -943,6 +948,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
     for (int wv = 0; wv < wpc; ++wv) s += cta_rows[(size_t)wv * NE + e];
     out[e] = s;
   }
+  sweep_stamp(a, 1);
 }
 
 // out[e] = sum_p part[p][e]: thread x = entry, thread y = strided slice of the partials.

@@ -73,6 +73,7 @@ __device__ __forceinline__ float transpose_reduce_grp(float (&p)[VN], int lane) 
 // (the stage goes back to the copy engine after the forward loads) instead of being read twice.
 template <int K, int NJ, int LPR, bool HOLD, bool BWD, int SPEC>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const __grid_constant__ SweepArgs a) {
+  sweep_stamp(a, 0);
   static_assert(K >= 2 && K <= kSubMaxK && NJ >= 1 && LPR * NJ <= kSubMaxChunks, "shape");
   static_assert(LPR == 8 || LPR == 16, "lanes per row");
   constexpr int RT = kSubRows;
@@ -472,6 +473,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
     for (int wv = 0; wv < wpc; ++wv) s += cta_rows[(size_t)wv * NE + e];
     out[e] = s;
   }
+  sweep_stamp(a, 1);
 }
 
 }  // namespace rfb

@@ -89,6 +89,13 @@ class Engine:
         return n.value
 
     @property
+    def last_project_h2d_bytes(self):
+        """Bytes the last `Block.project` call on this engine copied host -> device."""
+        v = C.c_double()
+        check(self.lib.rfb_engine_last_project_h2d_bytes(self.handle, C.byref(v)))
+        return v.value
+
+    @property
     def stream(self):
         s = C.c_uint64()
         check(self.lib.rfb_engine_stream(self.handle, C.byref(s)))
@@ -99,7 +106,10 @@ class Engine:
 
         torch.distributed is only the bootstrap (it broadcasts the 128-byte NCCL id); the
         per-iteration all-reduce is issued by the engine itself inside its CUDA graph."""
-        import torch.distributed as dist
+        try:
+            import torch.distributed as dist
+        except ImportError:          # torch is only the multi-GPU bootstrap; single-GPU use needs NumPy alone
+            return self
 
         if not dist.is_initialized() or dist.get_world_size() == 1 or self.world > 1:
             return self
@@ -211,7 +221,17 @@ class Block:
         return self.shape[0]
 
     def __matmul__(self, other):
-        return np.asarray(self) @ np.asarray(other)
+        """`XS @ b` (rfest/GLM/_glm.py:562): computed on the device (rfb_block_matmul); only the
+        (n_rows, k) product comes back, the block never leaves HBM."""
+        B = np.asarray(other, dtype=np.float32)
+        vec = B.ndim == 1
+        B2 = np.ascontiguousarray(B.reshape(B.shape[0], -1))
+        if B2.shape[0] != self.shape[1]:
+            raise ValueError(f"matmul: block has {self.shape[1]} columns, operand {B2.shape[0]} rows")
+        out = np.empty((self.shape[0], B2.shape[1]), dtype=np.float32)
+        check(self.lib.rfb_block_matmul(self.handle, B2.ctypes.data_as(C.c_void_p), int(B2.shape[1]),
+                                        out.ctypes.data_as(C.c_void_p)))
+        return out[:, 0] if vec else out
 
 
 class DeviceVector:
@@ -219,12 +239,16 @@ class DeviceVector:
     reference keeps JAX device arrays there).  Behaves like an array where the GLM API needs it:
     `shape`, `len()`, indexing and `np.asarray()` copy it back (once), `as_torch()` is zero-copy."""
 
-    def __init__(self, engine, device_ptr, n):
+    def __init__(self, engine, device_ptr, n, padded_source=False):
         self.n = int(n)
         self.shape = (self.n,)
         self.dtype = np.dtype(np.float32)
         self._block = Block(engine, max(1, (self.n + 3) // 4), 4)   # contiguous n floats (+ padding)
         if device_ptr is not None and self.n > 0:
+            # rfb_block_write moves whole 4-float rows: the source must hold the padded length
+            if self.n % 4 and not padded_source:
+                raise ValueError("DeviceVector: n is not a multiple of 4 and the source is not padded; "
+                                 "pass padded_source=True if it holds (n + 3) // 4 * 4 floats")
             check(engine.lib.rfb_block_write(self._block.handle, 0, (self.n + 3) // 4,
                                              C.c_void_p(int(device_ptr)), 1))
         self._host = None
@@ -408,6 +432,12 @@ class DeviceModel:
         """-> mean ms of (train sweep, dev sweep, reduction + all-reduce, update) over n iterations."""
         ms = np.zeros(4, dtype=np.float64)
         check(self.lib.rfb_fit_run_timed(self.handle, int(n), ms.ctypes.data_as(_lib._dp)))
+        return ms
+
+    def fit_sweep_times(self, kind, i0, n):
+        """-> ms of the `kind` sweep kernel in iterations [i0, i0 + n), stamped inside the replayed graph."""
+        ms = np.zeros(n, dtype=np.float64)
+        check(self.lib.rfb_fit_sweep_times(self.handle, _lib.KIND[kind], int(i0), int(n), ms.ctypes.data_as(_lib._dp)))
         return ms
 
     def fit_finish(self, i_last):

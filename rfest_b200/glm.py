@@ -21,6 +21,7 @@ NumPy's generator because `jax.random` cannot be reproduced without JAX.
 """
 
 import time
+import warnings
 
 import numpy as np
 
@@ -100,6 +101,9 @@ class GLM:
         always computes in float32 (the reference's fp32 JAX path)."""
         if distr not in _lib.DISTR:
             raise NotImplementedError(distr)                                   # _glm.py:603
+        if np.dtype(dtype) != np.float32:
+            warnings.warn(f"rfest_b200.GLM computes in float32 (the reference's fp32 path); dtype="
+                          f"{np.dtype(dtype).name} is accepted for API compatibility only", stacklevel=2)
         if output_nonlinearity not in _lib.NL:
             raise NotImplementedError(
                 f"Input filter nonlinearity `{output_nonlinearity}` is not supported.")
@@ -463,8 +467,15 @@ class GLM:
         n = float(self._n_trim["train"])
         gaussian = self.distr == "gaussian"
         if gaussian:
-            _, sums = self._dm.eval("train", b_flat, ic)
-            rss = sums[_lib.SUM_SQERR]                                            # _glm.py:1070-1071
+            # _glm.py:1068-1071: the residuals of `y_pred[w_type]['train']` -- after a fit that is the
+            # LAST iteration's prediction (:832), not the selected model's; reproduced as is
+            held = self.y_pred.get(w_type, {}).get("train")
+            if held is not None and len(held) == self._n_rows["train"]:
+                rss, _ = self._dm.loss_of_predictions("train", held)
+            else:
+                _, sums = self._dm.eval("train", b_flat, ic)
+                rss = sums[_lib.SUM_SQERR]
+            # (both entry points return sums over all ranks)
         V, b_se, w_se = {}, {}, {}
         for i, name in enumerate(self.filter_names):
             k = self.n_features[name]
@@ -915,7 +926,16 @@ class GLM:
         else:
             y_pred = self.predict({"stimulus": X_test}, w_type)
         if self.engine.world > 1:
+            # every rank predicts its shard of the test set; the score is the global one, from
+            # all-reduced sums (the same closed forms the device uses for the fit's metric traces)
             lo, hi = self._row_range["test"]
-            y_test = y_test[lo:hi]
-        s = self.compute_score(y_test, y_pred, metric)
+            y_loc = np.asarray(y_test[lo:hi], dtype=np.float64)
+            r = np.asarray(y_pred, dtype=np.float64)
+            sums = self.engine.allreduce_f64([len(y_loc), y_loc.sum(), (y_loc * y_loc).sum(), r.sum(),
+                                              (r * r).sum(), (y_loc * r).sum(), ((y_loc - r) ** 2).sum()])
+            s = _metrics.score_from_sums(metric, *sums)
+            if s is None:
+                print(f"Metric `{metric}` is not supported.")
+        else:
+            s = self.compute_score(y_test, y_pred, metric)
         return (s, y_pred) if return_prediction else s

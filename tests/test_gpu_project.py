@@ -220,3 +220,102 @@ def test_tensor_core_spatial_projection(n, n_pix, n_q):
     assert np.abs(out[0] - ref).max() <= 2e-6 * scale
     assert np.abs(out[1] - ref).max() <= 2e-6 * scale          # fp32-level accuracy from tf32 tensor cores
     assert not np.array_equal(out[0], out[1])                   # i.e. the tensor-core path really ran
+
+
+# ---- round 2: wide time bases, the host -> device staging ring, block @ matrix ----------------------------
+@pytest.mark.parametrize("nlag,n_pix", [(20, 1), (37, 1), (24, 3), (70, 2)])
+def test_filters_without_basis_wider_than_16_lags(nlag, n_pix):
+    """a filter without a spline basis hands the kernel St = I[nlag]; more than 16 temporal
+    columns used to be refused.  Integer input must still come back exactly (rfest/utils.py:50-67)."""
+    rng = np.random.default_rng(nlag)
+    shape = (333,) if n_pix == 1 else (333, n_pix)
+    stim = rng.integers(-9, 10, size=shape).astype(np.float32)
+    m = _glm(distr="gaussian")
+    m.add_design_matrix(stim, dims=[nlag] if n_pix == 1 else [nlag, n_pix], smooth=None, shift=1, name="history")
+    got = m._blocks["train"]["history"].read()
+    want = design.trimmed_design(stim.reshape(333, -1), nlag, 1, m.burn_in, dtype=np.float32)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert m.n_features["history"] == nlag * n_pix
+
+
+def test_spline_basis_with_more_than_16_temporal_functions():
+    rng = np.random.default_rng(3)
+    stim = rng.standard_normal((400, 5)).astype(np.float32)
+    m = _glm(distr="gaussian")
+    m.add_design_matrix(stim, dims=[40, 5], df=[21, 3], smooth="cr", name="stimulus")
+    ref = _oracle_xs(stim, [40, 5], [21, 3], 0, 39)
+    got = np.asarray(m.XS["train"]["stimulus"])
+    assert got.shape == ref.shape == (361, 63)
+    assert np.abs(got - ref).max() <= 3e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("slab_rows", [4096, 5000, 1 << 15])
+def test_host_ring_equals_device_input_bit_for_bit(slab_rows):
+    """Host arrays travel through the 3-slot pinned ring (copy stream + events) in slabs; the result
+    must not depend on the slab size, on pageable vs pinned source memory, or on host vs device input."""
+    import torch
+
+    from rfest_b200.engine import Engine, pinned_empty
+
+    rng = np.random.default_rng(21)
+    n = 23000
+    stim = rng.standard_normal((n, 20, 15)).astype(np.float32)
+    eng = Engine.get()
+    outs = []
+    try:
+        for src in ("device", "pageable", "pinned", "serial"):
+            eng.set_option("project_slab_rows", slab_rows)
+            eng.set_option("h2d_overlap", 0 if src == "serial" else 1)
+            if src == "device":
+                x = torch.from_numpy(stim).cuda()
+            elif src == "pinned":
+                x = pinned_empty(stim.size).reshape(stim.shape)
+                x[...] = stim
+            else:
+                x = stim
+            m = _glm(distr="gaussian")
+            m.add_design_matrix(x, dims=[25, 20, 15], df=[8, 6, 6], smooth="cr", name="stimulus")
+            outs.append(np.asarray(m.XS["train"]["stimulus"]))
+            if src != "device":
+                assert eng.last_project_h2d_bytes >= stim.nbytes
+    finally:
+        eng.set_option("project_slab_rows", 0)
+        eng.set_option("h2d_overlap", 1)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+    ref = _oracle_xs(stim[:300], [25, 20, 15], [8, 6, 6], 0, 24)
+    assert np.abs(outs[0][:276] - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_block_matmul_runs_on_the_device():
+    rng = np.random.default_rng(2)
+    stim = rng.standard_normal((5000, 6, 5)).astype(np.float32)
+    m = _glm(distr="gaussian")
+    m.add_design_matrix(stim, dims=[7, 6, 5], df=[4, 3, 3], smooth="cr", name="stimulus")
+    blk = m.XS["train"]["stimulus"]
+    XS = np.asarray(blk).astype(np.float64)
+    launches = m.engine.launch_count
+    for k in (1, 3, 11):
+        B = rng.standard_normal((36, k)).astype(np.float32)
+        got = blk @ B
+        assert got.shape == (XS.shape[0], k) and got.dtype == np.float32
+        ref = XS @ B.astype(np.float64)
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    v = blk @ B[:, 0]
+    assert v.shape == (XS.shape[0],)
+    assert m.engine.launch_count > launches                 # a kernel ran; nothing was multiplied on the host
+    with pytest.raises(ValueError):
+        blk @ np.zeros((35, 1), np.float32)
+
+
+def test_refusals_are_pinned():
+    """`softmax` as a FILTER nonlinearity (a normalisation over all samples per filter, _glm.py:134-140
+    reached from :561-565) is refused -- documented in INTEGRATION.md; float64 is accepted with a warning."""
+    stim = np.zeros((50, 3), np.float32)
+    m = _glm(distr="poisson", output_nonlinearity="softmax")          # as the OUTPUT nonlinearity it exists
+    with pytest.raises(NotImplementedError):
+        m.add_design_matrix(stim, dims=[4, 3], df=[3, 3], smooth="cr", filter_nonlinearity="softmax")
+    with pytest.raises(NotImplementedError):
+        m.add_design_matrix(stim, dims=[4, 3], df=[3, 3], smooth="cr", filter_nonlinearity="swish")
+    with pytest.warns(UserWarning, match="float32"):
+        _glm(distr="gaussian", dtype=np.float64)

@@ -55,6 +55,12 @@ def test_engine_matches_reference_outputs(golden_glm, name):
     assert gc.data_digest(data) == str(golden_glm[f"{name}/digest"]), "inputs differ from the fixture's"
     m, extra = gc.run_case(lambda d, o: GLM(distr=d, output_nonlinearity=o), name, np.float32, data=data)
     got = gc.summarize(m, extra)
+    # how far the reference's own float32 run ends from its float64 run: where that alone exceeds
+    # the north star's 1e-4 (mle_3d_exp: 4.5e-4 -- an ill-conditioned direction of the weights, the
+    # losses agree to 5e-6) no float32 implementation can be held to 1e-4, so the bound scales
+    ref64, ref32 = _case(golden_glm, name, "f64"), _case(golden_glm, name, "f32")
+    spread = max(_wrel(ref32[f"last.{f}"], ref64[f"last.{f}"]) for f in ref64["filter_names"].tolist())
+    weight_rtol = max(WEIGHT_RTOL, 3 * spread)
     for tag in ("f64", "f32"):
         want = _case(golden_glm, name, tag)
         assert got["filter_names"].tolist() == want["filter_names"].tolist()
@@ -73,15 +79,15 @@ def test_engine_matches_reference_outputs(golden_glm, name):
         gb, wb = int(got["best_iteration"]), int(want["best_iteration"])
         assert gb == wb or abs(trace[gb] - trace[wb]) < 1e-5 * abs(want["cost_train"][0]), (gb, wb)
         for fname in want["filter_names"].tolist():
-            assert _wrel(got[f"last.{fname}"], want[f"last.{fname}"]) < WEIGHT_RTOL, (tag, fname)
+            assert _wrel(got[f"last.{fname}"], want[f"last.{fname}"]) < weight_rtol, (tag, fname)
             if gb == wb:
-                assert _wrel(got[f"w.{fname}"], want[f"w.{fname}"]) < WEIGHT_RTOL, (tag, fname)
+                assert _wrel(got[f"w.{fname}"], want[f"w.{fname}"]) < weight_rtol, (tag, fname)
         for kind in ("train", "dev"):
             if f"y_pred.{kind}" in want:
-                assert _wrel(got[f"y_pred.{kind}"], want[f"y_pred.{kind}"]) < 1e-4, (tag, kind)
+                assert _wrel(got[f"y_pred.{kind}"], want[f"y_pred.{kind}"]) < weight_rtol, (tag, kind)
         if c["test"] and gb == wb:
             assert abs(float(got["test_score"]) - float(want["test_score"])) < 1e-4
-            assert _wrel(got["test_pred"], want["test_pred"]) < 1e-4
+            assert _wrel(got["test_pred"], want["test_pred"]) < weight_rtol
         if c["compute_ci"] and gb == wb:
             for fname in want["filter_names"].tolist():
                 # inverse of a Gram matrix: conditioning amplifies float32 rounding

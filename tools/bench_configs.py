@@ -41,7 +41,9 @@ CONFIGS = {
 }
 
 
-def run(cid):
+def run(cid, iters=None, quiet=False):
+    """Set up configuration `cid` on GPU 0 with device-generated data, time `iters` graph-replayed fit
+    iterations with CUDA events and read the sweeps' in-graph %globaltimer durations.  -> dict."""
     c = CONFIGS[cid]
     eng = Engine.get(0)
     dims, n_raw = c["dims"], c["n_raw"]
@@ -74,8 +76,8 @@ def run(cid):
     m._sync()
     dm = m._dm
     dm.set_params(*m._flatten(m.p0))
-    K, W = c["iters"], 3
-    dm.fit_begin(np.full(W + 2 * K, c["step"]), c["alpha"], c["beta"], "corrcoef")
+    K, W = iters or c["iters"], 3
+    dm.fit_begin(np.full(W + K, c["step"]), c["alpha"], c["beta"], "corrcoef")
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda:0"))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dm.fit_run(W)
@@ -85,27 +87,98 @@ def run(cid):
     ev1.record(ext)
     eng.synchronize()
     ms = ev0.elapsed_time(ev1) / K
-    ms4 = dm.fit_run_timed(K)
-    dm.fit_finish(W + 2 * K - 1)
-    tr = dm.fit_traces(W + 2 * K)
+    sweep_tr = float(np.mean(dm.fit_sweep_times("train", W, K)))
+    sweep_dv = float(np.mean(dm.fit_sweep_times("dev", W, K))) if c["dev"] > 0 else 0.0
+    dm.fit_finish(W + K - 1)
+    tr = dm.fit_traces(W + K)
     dm.fit_end()
     n_train = n_tr - burn
     n_dev = (n_raw - n_tr - burn) if c["dev"] > 0 else 0
     C = int(np.prod(c["df"])) + (8 if c["history"] else 0)
     b_iter = 4.0 * (n_train + n_dev) * (C + 1)
-    out = {"config": c["name"], "iterations_per_s": 1e3 / ms, "ms_per_iter": ms,
-           "kernel_ms": {"train_sweep": ms4[0], "dev_sweep": ms4[1], "reduce": ms4[2], "update": ms4[3]},
+    out = {"config": c["name"], "iterations_per_s": 1e3 / ms, "ms_per_iter": ms, "iters_timed": K,
+           "sweep_ms_in_graph": {"train": sweep_tr, "dev": sweep_dv},
            "algorithmic_GB_per_iter": b_iter / 1e9,
            "achieved_GBps_whole_iteration": b_iter / ms / 1e6,
-           "achieved_GBps_train_sweep": 4.0 * n_train * (C + 1) / ms4[0] / 1e6,
-           "frac_of_measured_6551": b_iter / ms / 1e6 / 6551, "setup_s": setup_s,
+           "achieved_GBps_train_sweep": 4.0 * n_train * (C + 1) / sweep_tr / 1e6,
+           "frac_of_measured_peak": b_iter / ms / 1e6 / PEAK_GBS,
+           "train_sweep_frac_of_measured_peak": 4.0 * n_train * (C + 1) / sweep_tr / 1e6 / PEAK_GBS,
+           "setup_s": setup_s,
            "loss_first_last": [float(tr[0][0]), float(tr[0][-1])]}
-    print(json.dumps(out), flush=True)
+    if not quiet:
+        print(json.dumps(out), flush=True)
     del m, dm, stim, y
     import gc
 
     gc.collect()
     torch.cuda.empty_cache()
+    return out
+
+
+def projection(dims, df, log2n, reps=3):
+    """K1 alone: `add_design_matrix` of a DEVICE-resident stimulus of 2^log2n frames (spatial tcgen05
+    GEMM + temporal step), CUDA-event timed.  Bytes = frames read + projected rows written."""
+    eng = Engine.get(0)
+    n = 1 << log2n
+    n_pix = int(np.prod(dims[1:]))
+    stim = torch.randn((n, n_pix), device="cuda:0", dtype=torch.float32)
+    ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda:0"))
+    best = None
+    for _ in range(reps):
+        m = GLM(distr="gaussian", device=0)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(ext)
+        m.add_design_matrix(stim, dims=dims, df=df, smooth="cr", name="stimulus")
+        ev1.record(ext)
+        eng.synchronize()
+        t = ev0.elapsed_time(ev1)
+        best = t if best is None else min(best, t)
+        del m
+    cols = int(np.prod(df))
+    byts = 4.0 * n * n_pix + 4.0 * (n - dims[0] + 1) * cols
+    flops = 2.0 * n * n_pix * int(np.prod(df[1:])) + 2.0 * n * cols * dims[0]
+    del stim
+    torch.cuda.empty_cache()
+    return {"dims": dims, "df": df, "frames": n, "ms": best, "GBps_in_plus_out": byts / best / 1e6,
+            "frac_of_measured_peak": byts / best / 1e6 / PEAK_GBS, "separable_TFLOPs": flops / best / 1e9}
+
+
+def host_projection(dims, df, log2n):
+    """`add_design_matrix(<host ndarray>)`: the frames cross PCIe through the engine's pinned 3-slot ring
+    (copy stream overlapped with the projection kernels).  Wall clock, pageable source."""
+    eng = Engine.get(0)
+    n = 1 << log2n
+    frame = tuple(dims[1:])
+    host = np.empty((n,) + frame, dtype=np.float32)
+    step = 1 << 20
+    for k0 in range(0, n, step):                                # generated on the device, copied out
+        k1 = min(n, k0 + step)
+        host[k0:k1] = torch.randn((k1 - k0,) + frame, device="cuda:0").cpu().numpy()
+    out = {}
+    for label, overlap in (("ring", 1), ("serial_r1", 0)):
+        eng.set_option("h2d_overlap", overlap)
+        best = None
+        for _ in range(2):
+            m = GLM(distr="gaussian", device=0)
+            eng.synchronize()
+            t0 = time.perf_counter()
+            m.add_design_matrix(host, dims=dims, df=df, smooth="cr", name="stimulus")
+            eng.synchronize()
+            t = time.perf_counter() - t0
+            best = t if best is None else min(best, t)
+            del m
+        out[label] = {"wall_s": best, "h2d_GBps": host.nbytes / best / 1e9}
+    eng.set_option("h2d_overlap", 1)
+    out.update({"frames": n, "host_GB": host.nbytes / 1e9, "source": "pageable numpy array"})
+    return out
+
+
+try:
+    PEAK_GBS = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                 "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK_GBS = 6551.0
 
 
 if __name__ == "__main__":
