@@ -235,6 +235,11 @@ int rfb_fit_run(rfb_model* m, int n_iters);
  * around each kernel: ms4 = mean milliseconds of {train sweep, dev sweep, reduction + all-reduce,
  * update}.  For bench.py's per-kernel roofline. */
 int rfb_fit_run_timed(rfb_model* m, int n_iters, double* ms4);
+/* 1 when the fit in progress runs as the persistent small-model kernel: data sets that fit the SMs'
+ * shared memory (launch-latency regime, e.g. the reference README recipe) run every batch of
+ * rfb_fit_run iterations as ONE cooperative kernel with grid barriers instead of a graph per iteration
+ * (engine option "fit_persistent": 0 off, 1 auto, 2 whenever the data fit). */
+int rfb_fit_is_persistent(rfb_model* m, int* out);
 /* Duration (ms) of the train / dev sweep kernel of iterations [i0, i0 + n), measured INSIDE the
  * replayed graph: every CTA of a sweep folds %globaltimer into a per-iteration (first entry, last exit)
  * pair, so these are the kernel times of the very iterations rfb_fit_run executed (no events, no

@@ -75,6 +75,7 @@ SIGNATURES = {
     "rfb_fit_begin": (_i, [_p, _i, _p, _d, _d, _i]),
     "rfb_fit_run": (_i, [_p, _i]),
     "rfb_fit_run_timed": (_i, [_p, _i, _dp]),
+    "rfb_fit_is_persistent": (_i, [_p, _ip]),
     "rfb_fit_sweep_times": (_i, [_p, _i, _i, _i, _dp]),
     "rfb_fit_iterations": (_i, [_p, _ip]),
     "rfb_fit_finish": (_i, [_p, _i]),

@@ -21,8 +21,10 @@
 #include "project_tc.cuh"
 #include "sweep.cuh"
 #include "sweep_sub.cuh"
+#include "sweep_sub2.cuh"
 #include "softmax.cuh"
 #include "update.cuh"
+#include "fit_small.cuh"
 
 using namespace rfb;
 
@@ -122,9 +124,12 @@ struct rfb_engine {
   void* ring_dev[kRingSlots] = {};
   size_t ring_bytes = 0;
   cudaEvent_t ring_copied[kRingSlots] = {}, ring_consumed[kRingSlots] = {};
-  int h2d_threads = 4;    // host threads filling a pinned slot from pageable memory
+  int h2d_threads = 8;    // host threads filling a pinned slot from pageable memory
   int h2d_overlap = 1;    // 0: the round-1 path (one staging buffer, synchronous per slab) for comparison
   double last_project_h2d_bytes = 0.0;
+  int sweep_pool_ctas = 0;     // CTAs of the pooled subunit sweep (0: one per SM); tests shrink it to force stage reuse
+  int fit_small_ctas = 0;      // CTAs of the persistent small-model kernel (0: sized from the row count)
+  int fit_persistent = 1;      // small models: one persistent cooperative kernel for the whole loop (fit_small.cuh)
   int project_slab_rows = 0;   // rows per projection slab (0: sized from the frame size); tests shrink it
   int project_tc = 1;     // spatial projection on tensor cores (tcgen05, 3xTF32) when the shape allows
   // one-shot NVLink exchange (multi-GPU): local buffer, peers' mappings, device counters
@@ -204,6 +209,12 @@ struct SweepBuffers {
   size_t smem = 0;
   int sub = 0;        // this data set runs the subunit sweep: variant (see sub_instance), 0 = no
   int sub_nj = 0;
+  // gradient sweeps of subunit models on the stage-pool / tensor-memory kernel (sweep_sub2.cuh)
+  bool pool = false;
+  int pool_ncw = 0;   // consumer warps per CTA
+  int pool_grid = 0, pool_stages = 0;
+  size_t pool_smem = 0;
+  int cur_grid = 0;   // CTAs (= partial rows) of the sweep launched last: what the reduction adds up
 };
 
 // subunit pattern: K heads whose columns are ONE shared block, at most one other head on <= 8 chunks
@@ -261,8 +272,17 @@ struct Fit {
   UpdateArgs ua{};
   bool finished = false;
   // %globaltimer stamps of the sweeps, written inside the replayed graph: [2 kinds][max_iters + 1][start, end]
+  float* bc_f = nullptr;        // Adam bias corrections per iteration (see UpdateArgs)
+  double* bc_d = nullptr;
   unsigned long long* stamps = nullptr;
   bool stamp_now = false;       // set while enqueue_iteration builds / launches an iteration
+  // small models: the whole loop as one persistent cooperative kernel (fit_small.cuh)
+  bool small = false;
+  SmallArgs sa{};
+  double* small_part = nullptr;
+  int small_grid = 0;
+  size_t small_smem = 0;
+  const void* small_fn = nullptr;
 };
 
 struct rfb_model {
@@ -307,13 +327,13 @@ static SweepFn pick_variant(bool bwd, bool staged, int spec) {
   return pick_staged<H, NCH, RB, 0>(bwd);
 }
 
-template <int K, int NJ, int LPR, bool HOLD>
+template <int K, int NJ, int LPR, bool HOLD, bool TM = false>
 static SweepFn pick_sub(bool bwd, int spec) {
   if (spec == 1)
-    return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, LPR, HOLD, true, 1>
-               : (SweepFn)sweep_subunit_kernel<K, NJ, LPR, false, false, 1>;
-  return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, LPR, HOLD, true, 0>
-             : (SweepFn)sweep_subunit_kernel<K, NJ, LPR, false, false, 0>;
+    return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, LPR, HOLD, true, 1, TM>
+               : (SweepFn)sweep_subunit_kernel<K, NJ, LPR, false, false, 1, false>;
+  return bwd ? (SweepFn)sweep_subunit_kernel<K, NJ, LPR, HOLD, true, 0, TM>
+             : (SweepFn)sweep_subunit_kernel<K, NJ, LPR, false, false, 0, false>;
 }
 // variant 3 (default, all shapes): 16 lanes per row, rows read twice from the stage.  For 4 subunits the two
 // mappings it was measured against are kept: 1 = 8 lanes per row, 2 = 16 lanes per row with the rows held in
@@ -330,6 +350,23 @@ static SweepFn sub_instance(int variant, int K, int NJ, bool bwd, int spec) {
   INST(2, 4, 1, 16, true) INST(2, 4, 5, 16, true)
   INST(3, 2, 1, 16, false) INST(3, 3, 1, 16, false) INST(3, 4, 1, 16, false)
   INST(3, 2, 5, 16, false) INST(3, 3, 5, 16, false) INST(3, 4, 5, 16, false)
+#undef INST
+  // 6: accumulators in tensor memory + rows held in registers between the passes; 7: tensor memory only
+#define INSTT(v, k, nj, hold) \
+  if (variant == v && K == k && NJ == nj) return pick_sub<k, nj, 16, hold, true>(bwd, spec);
+  INSTT(6, 2, 1, true) INSTT(6, 3, 1, true) INSTT(6, 4, 1, true) INSTT(6, 2, 5, true) INSTT(6, 3, 5, true) INSTT(6, 4, 5, true)
+  INSTT(7, 2, 1, false) INSTT(7, 3, 1, false) INSTT(7, 4, 1, false) INSTT(7, 2, 5, false) INSTT(7, 3, 5, false) INSTT(7, 4, 5, false)
+#undef INSTT
+  return nullptr;
+}
+
+static SweepFn pool_instance(int K, int NJ, int spec, int ncw) {
+#define INST(k, nj)                                                                                              \
+  if (K == k && NJ == nj) {                                                                                      \
+    if (ncw == 15) return spec == 1 ? (SweepFn)sweep_subunit_pool_kernel<k, nj, 1, 15> : (SweepFn)sweep_subunit_pool_kernel<k, nj, 0, 15>; \
+    return spec == 1 ? (SweepFn)sweep_subunit_pool_kernel<k, nj, 1, 12> : (SweepFn)sweep_subunit_pool_kernel<k, nj, 0, 12>;              \
+  }
+  INST(2, 1) INST(3, 1) INST(4, 1) INST(2, 5) INST(3, 5) INST(4, 5)
 #undef INST
   return nullptr;
 }
@@ -565,7 +602,7 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
   if (p.sub.ok && e->sweep_sub && e->sweep_staged && all_slots) {
     // subunit sweep (sweep_sub.cuh): 8-row tiles, rows stay in the stage through both passes
     const SubPlan& sp = p.sub;
-    int variant = std::min(std::max(e->sweep_sub, 1), 3);
+    int variant = (e->sweep_sub == 6 || e->sweep_sub == 7) ? e->sweep_sub : std::min(std::max(e->sweep_sub, 1), 3);
     if (variant <= 2 && sp.K != 4) variant = 3;        // the comparison variants exist for 4 subunits only
     const int NJ = sub_template_nj(variant, sp.c0), cpl = sub_lpr(variant) * NJ;
     int st = e->sweep_stages > 0 ? e->sweep_stages : 2;
@@ -611,6 +648,57 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
       sb.smem = smem;
       sb.sub = variant;
       sb.sub_nj = NJ;
+      if (e->sweep_sub >= 4 && variant == 3) {
+        // gradient sweeps: 15 (sweep_sub = 4) or 12 (= 5) consumer warps + 1 producer per SM, as many pooled
+        // stages as shared memory holds
+        const int ncw = e->sweep_sub == 5 ? 12 : 15;
+        const int nthreads = sub2_threads(ncw);
+        int ps = e->sweep_stages > 0 ? e->sweep_stages : 64;
+        size_t psmem = 0;
+        bool pfits = false;
+        for (; ps >= ncw + 2 && !pfits; --ps) {
+          psmem = sweep_sub2_smem_bytes(ps, p.ctot, sp.K, cpl, sp.c0);
+          if (psmem > 227 * 1024) continue;
+          pfits = true;
+          for (int spec = 0; spec < 2 && pfits; ++spec) {
+            SweepFn fn = pool_instance(sp.K, NJ, spec, ncw);
+            if (!fn || cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem) != cudaSuccess) {
+              cudaGetLastError();
+              pfits = false;
+              break;
+            }
+            int o = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, nthreads, psmem) != cudaSuccess || o < 1) {
+              cudaGetLastError();
+              pfits = false;
+            }
+          }
+          if (pfits) break;
+        }
+        if (pfits) {
+          int64_t pgrid = std::max<int64_t>(1, std::min<int64_t>(e->num_sms, (ntiles + ncw - 1) / ncw));
+          if (e->sweep_pool_ctas > 0) pgrid = std::min<int64_t>(pgrid, e->sweep_pool_ctas);
+          const size_t wbytes = sizeof(double) * (size_t)pgrid * ncw * p.NE;
+          const size_t cbytes = sizeof(double) * (size_t)pgrid * p.NE;
+          if (wbytes > sb.warp_acc_bytes) {
+            cudaFree(sb.warp_acc);
+            sb.warp_acc = nullptr;
+            CU(cudaMalloc(&sb.warp_acc, wbytes));
+            sb.warp_acc_bytes = wbytes;
+          }
+          if (cbytes > sb.cta_part_bytes) {
+            cudaFree(sb.cta_part);
+            sb.cta_part = nullptr;
+            CU(cudaMalloc(&sb.cta_part, cbytes));
+            sb.cta_part_bytes = cbytes;
+          }
+          sb.pool = true;
+          sb.pool_ncw = ncw;
+          sb.pool_grid = (int)pgrid;
+          sb.pool_stages = ps;
+          sb.pool_smem = psmem;
+        }
+      }
       return RFB_OK;
     }
   }
@@ -672,27 +760,11 @@ static int ensure_sweep_buffers(rfb_model* m, int kind) {
 
 // Launch one sweep over data set `kind` with the parameter image `ps`.  Leaves the per-CTA
 // partial sums in m->sb[kind].cta_part (grid rows).
-static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* head_nl, bool bwd,
-                        float* r_out, int out_nl_override = -1, const float* softmax = nullptr) {
+// The kernel-independent part of a sweep's arguments: where the rows, the response and the parameters are.
+static SweepArgs make_sweep_args(const rfb_model* m, int kind, const ParamSet& ps, const int* head_nl,
+                                 int out_nl_override, const float* softmax) {
   const Plan& p = m->plan;
-  DataSet& ds = m->data[kind];
-  rfb_engine* e = m->e;
-  int RB = p.RB;
-  TRY(ensure_sweep_buffers(m, kind));
-  SweepBuffers& sb = m->sb[kind];
-  SweepFn fn = nullptr;
-  const int eff_out_nl = out_nl_override >= 0 ? out_nl_override : m->out_nl;
-  if (sb.sub) {
-    int spec = (m->distr == RFB_DISTR_POISSON && eff_out_nl == RFB_NL_SOFTPLUS) ? 1 : 0;
-    for (int k = 0; k < p.sub.K; ++k)
-      if (head_nl[p.sub.heads[k]] != RFB_NL_SOFTPLUS) spec = 0;
-    fn = sub_instance(sb.sub, p.sub.K, sb.sub_nj, bwd, spec);
-    if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no subunit sweep instance");
-  } else if (!p.generic) {
-    fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, sweep_spec(m, head_nl), &RB);
-    if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
-  }
-
+  const DataSet& ds = m->data[kind];
   SweepArgs a{};
   a.n_slots = p.n_slots;
   for (int s = 0; s < p.n_slots; ++s) {
@@ -715,20 +787,54 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   a.softmax = softmax;
   a.distr = m->distr;
   a.two_over_n = ds.n_total > 0 ? (float)(2.0 / ds.n_total) : 0.f;
+  a.layout_heads = p.Ht;
+  a.sub_slot = p.sub.slot;
+  for (int k = 0; k < kSubMaxK; ++k) a.sub_head[k] = p.sub.heads[k];
+  a.sub_extra_head = p.sub.extra_head;
+  return a;
+}
+
+static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* head_nl, bool bwd,
+                        float* r_out, int out_nl_override = -1, const float* softmax = nullptr) {
+  const Plan& p = m->plan;
+  rfb_engine* e = m->e;
+  int RB = p.RB;
+  TRY(ensure_sweep_buffers(m, kind));
+  SweepBuffers& sb = m->sb[kind];
+  SweepFn fn = nullptr;
+  const int eff_out_nl = out_nl_override >= 0 ? out_nl_override : m->out_nl;
+  if (sb.sub) {
+    int spec = (m->distr == RFB_DISTR_POISSON && eff_out_nl == RFB_NL_SOFTPLUS) ? 1 : 0;
+    for (int k = 0; k < p.sub.K; ++k)
+      if (head_nl[p.sub.heads[k]] != RFB_NL_SOFTPLUS) spec = 0;
+    fn = sub_instance(sb.sub, p.sub.K, sb.sub_nj, bwd, spec);
+    if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no subunit sweep instance");
+  } else if (!p.generic) {
+    fn = sweep_instance(p.Ht, p.NCH, bwd, sb.staged != 0, sweep_spec(m, head_nl), &RB);
+    if (!fn) return fail(RFB_ERR_UNSUPPORTED, "no sweep kernel instance");
+  }
+
+  SweepArgs a = make_sweep_args(m, kind, ps, head_nl, out_nl_override, softmax);
   a.warp_acc = sb.warp_acc;
   a.cta_part = sb.cta_part;
   a.r_out = r_out;
   a.flush_tiles = std::max(1, 256 / RB);
   a.n_stages = sb.stages;
-  a.layout_heads = p.Ht;
-  a.sub_slot = p.sub.slot;
-  for (int k = 0; k < kSubMaxK; ++k) a.sub_head[k] = p.sub.heads[k];
-  a.sub_extra_head = p.sub.extra_head;
   if (m->fit.stamp_now && m->fit.stamps && kind <= RFB_KIND_DEV) {
     a.stamp = m->fit.stamps + (size_t)kind * 2 * ((size_t)m->fit.max_iters + 1);
     a.stamp_it = m->fit.it;
   }
-  if (sb.sub) {
+  sb.cur_grid = sb.grid;
+  if (sb.sub && sb.pool && bwd) {
+    int spec = (m->distr == RFB_DISTR_POISSON && eff_out_nl == RFB_NL_SOFTPLUS) ? 1 : 0;
+    for (int k = 0; k < p.sub.K; ++k)
+      if (head_nl[p.sub.heads[k]] != RFB_NL_SOFTPLUS) spec = 0;
+    SweepFn pfn = pool_instance(p.sub.K, sb.sub_nj, spec, sb.pool_ncw);
+    if (!pfn) return fail(RFB_ERR_UNSUPPORTED, "no pooled subunit sweep instance");
+    a.n_stages = sb.pool_stages;
+    pfn<<<sb.pool_grid, sub2_threads(sb.pool_ncw), sb.pool_smem, e->stream>>>(a);
+    sb.cur_grid = sb.pool_grid;
+  } else if (sb.sub) {
     fn<<<sb.grid, sb.threads, sb.smem, e->stream>>>(a);
   } else if (p.generic) {
     if (bwd) sweep_generic_kernel<true><<<sb.grid, sb.threads, 0, e->stream>>>(a, p.Ht);
@@ -746,12 +852,12 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
 static int launch_reduce(rfb_model* m, int kind0, int e0, int n0, double* out0, int kind1, int e1,
                          int n1, double* out1) {
   const Plan& p = m->plan;
-  ReduceSeg s0{m->sb[kind0].cta_part + e0, m->sb[kind0].grid, p.NE, n0, out0};
+  ReduceSeg s0{m->sb[kind0].cta_part + e0, m->sb[kind0].cur_grid, p.NE, n0, out0};
   const int blocks0 = (n0 + kReduceEx - 1) / kReduceEx;
   ReduceSeg s1{nullptr, 0, 0, 0, nullptr};
   int blocks1 = 0;
   if (kind1 >= 0) {
-    s1 = ReduceSeg{m->sb[kind1].cta_part + e1, m->sb[kind1].grid, p.NE, n1, out1};
+    s1 = ReduceSeg{m->sb[kind1].cta_part + e1, m->sb[kind1].cur_grid, p.NE, n1, out1};
     blocks1 = (n1 + kReduceEx - 1) / kReduceEx;
   }
   reduce_partials_kernel<<<blocks0 + blocks1, dim3(kReduceEx, kReduceEy), 0, m->e->stream>>>(s0, s1, blocks0);
@@ -831,6 +937,8 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   if (const char* v = getenv("RFB_XCHG")) e->use_xchg = atoi(v);
   if (const char* v = getenv("RFB_H2D_THREADS")) e->h2d_threads = std::max(1, atoi(v));
   if (const char* v = getenv("RFB_H2D_OVERLAP")) e->h2d_overlap = atoi(v);
+  if (const char* v = getenv("RFB_FIT_PERSISTENT")) e->fit_persistent = atoi(v);
+  if (const char* v = getenv("RFB_FIT_SMALL_CTAS")) e->fit_small_ctas = std::max(0, atoi(v));
   *out = e;
   return RFB_OK;
 }
@@ -847,6 +955,9 @@ extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) 
   else if (k == "xchg") e->use_xchg = value;
   else if (k == "h2d_threads") e->h2d_threads = std::max(1, value);
   else if (k == "h2d_overlap") e->h2d_overlap = value;
+  else if (k == "fit_persistent") e->fit_persistent = value;
+  else if (k == "sweep_pool_ctas") e->sweep_pool_ctas = std::max(0, value);
+  else if (k == "fit_small_ctas") e->fit_small_ctas = std::max(0, value);
   else if (k == "project_slab_rows") e->project_slab_rows = std::max(0, value);
   else return fail(RFB_ERR_INVALID, "unknown option '%s'", key);
   return RFB_OK;
@@ -1997,7 +2108,7 @@ static int fit_release(rfb_model* m) {
   if (f.graph) cudaGraphDestroy(f.graph);
   cudaFree(f.step); cudaFree(f.cost_train); cudaFree(f.cost_dev); cudaFree(f.metric_train);
   cudaFree(f.metric_dev); cudaFree(f.ring_b); cudaFree(f.ring_ic); cudaFree(f.it);
-  cudaFree(f.m); cudaFree(f.v); cudaFree(f.mi); cudaFree(f.vi); cudaFree(f.fin); cudaFree(f.stamps);
+  cudaFree(f.m); cudaFree(f.v); cudaFree(f.mi); cudaFree(f.vi); cudaFree(f.fin); cudaFree(f.stamps); cudaFree(f.small_part); cudaFree(f.bc_f); cudaFree(f.bc_d);
   f = Fit();
   return RFB_OK;
 }
@@ -2043,12 +2154,12 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   long long sum_lo = lo, sum_hi = (long long)p.NE + (f.has_dev ? kNumScalars : 0);
   if (xchg) {
     // reduction fused with the exchange: sums go straight into every rank's buffer over NVLink
-    ReduceSeg s0{m->sb[RFB_KIND_TRAIN].cta_part + lo, m->sb[RFB_KIND_TRAIN].grid, p.NE, n_train, nullptr};
+    ReduceSeg s0{m->sb[RFB_KIND_TRAIN].cta_part + lo, m->sb[RFB_KIND_TRAIN].cur_grid, p.NE, n_train, nullptr};
     const int blocks0 = (n_train + kReduceEx - 1) / kReduceEx;
     ReduceSeg s1{nullptr, 0, 0, 0, nullptr};
     int blocks1 = 0;
     if (f.has_dev) {
-      s1 = ReduceSeg{m->sb[RFB_KIND_DEV].cta_part + tail, m->sb[RFB_KIND_DEV].grid, p.NE, kNumScalars, nullptr};
+      s1 = ReduceSeg{m->sb[RFB_KIND_DEV].cta_part + tail, m->sb[RFB_KIND_DEV].cur_grid, p.NE, kNumScalars, nullptr};
       blocks1 = (kNumScalars + kReduceEx - 1) / kReduceEx;
     }
     reduce_exchange_kernel<<<blocks0 + blocks1, dim3(kReduceEx, kReduceEy), 0, e->stream>>>(
@@ -2071,6 +2182,62 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   e->launches++;
   CU(cudaGetLastError());
   if (ev) CU(cudaEventRecord(ev[4], e->stream));
+  return RFB_OK;
+}
+
+// Decide whether this fit runs as the persistent small-model kernel and size it.  Eligible: one GPU, no
+// output softmax, a register-resident head count, <= 64 design columns, and both data sets small enough
+// to live in the shared memory of one CTA per SM (the regime where the graph path is launch-bound).
+static int plan_small_fit(rfb_model* m) {
+  Fit& f = m->fit;
+  const Plan& p = m->plan;
+  rfb_engine* e = m->e;
+  f.small = false;
+  if (!e->fit_persistent || e->world > 1 || m->out_nl == RFB_NL_SOFTMAX || p.generic) return RFB_OK;
+  if (p.F > 100 || p.n_chunks > kSmallMaxChunks || !(p.Ht == 1 || p.Ht == 2 || p.Ht == 3 || p.Ht == 5)) return RFB_OK;
+  const DataSet& tr = m->data[RFB_KIND_TRAIN];
+  const DataSet& dev = m->data[RFB_KIND_DEV];
+  const int64_t n_dev = f.has_dev ? dev.n : 0;
+  const double bytes = 4.0 * (double)(tr.n + n_dev) * (p.ctot + 1);
+  if (bytes > 8.0 * 1024 * 1024 && e->fit_persistent < 2) return RFB_OK;     // 2: force (tests)
+  const void* fn = p.Ht == 1 ? (const void*)fit_small_kernel<1> : p.Ht == 2 ? (const void*)fit_small_kernel<2>
+                 : p.Ht == 3 ? (const void*)fit_small_kernel<3> : (const void*)fit_small_kernel<5>;
+    int lpr = 1;
+  while (lpr < p.n_chunks) lpr <<= 1;
+  const int rows_per_pass = (kSmallThreads / 32) * (32 / lpr);
+  // measured at config 1 (16k rows): 64 CTAs x 4 passes beat 32 x 8 and 125 x 2 (the barrier and the CTA-ordered
+  // totals grow with the grid, the row loop shrinks with it)
+  int64_t grid = std::min<int64_t>(e->num_sms, std::max<int64_t>(1, (tr.n + 4 * rows_per_pass - 1) / (4 * rows_per_pass)));
+  if (e->fit_small_ctas > 0) grid = std::min<int64_t>(e->num_sms, e->fit_small_ctas);
+  const int rows_tr = (int)((tr.n + grid - 1) / grid), rows_dv = (int)((n_dev + grid - 1) / grid);
+  const size_t smem = fit_small_smem_bytes(rows_tr, rows_dv, p.ctot, p.Ht, p.P, p.F);
+  if (smem > 200 * 1024) return RFB_OK;
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSmallThreads, smem));
+  if (occ < 1) return RFB_OK;
+  const size_t row = (size_t)p.NE + kNumScalars;
+  CU(cudaMalloc(&f.small_part, sizeof(double) * 2 * row * (size_t)grid));
+  CU(cudaMemsetAsync(f.small_part, 0, sizeof(double) * 2 * row * (size_t)grid, e->stream));
+  SmallArgs& sa = f.sa;
+  sa = SmallArgs{};
+  sa.tr = make_sweep_args(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), -1, nullptr);
+  if (f.has_dev) sa.dv = make_sweep_args(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), -1, nullptr);
+  else sa.dv.n_rows = 0;
+  sa.ua = f.ua;
+  sa.ua.final_only = 0;
+  sa.ua.x = xchg_args(e, false);
+  sa.ua.fin_local = f.fin;
+  sa.ua.sum_lo = 0;
+  sa.ua.sum_hi = 0;
+  sa.part = f.small_part;
+  sa.rows_tr = rows_tr;
+  sa.rows_dv = rows_dv;
+  sa.NE = p.NE;
+  f.small_grid = (int)grid;
+  f.small_smem = smem;
+  f.small_fn = fn;
+  f.small = true;
   return RFB_OK;
 }
 
@@ -2124,6 +2291,23 @@ extern "C" int rfb_fit_begin(rfb_model* m, int max_iters, const double* step_siz
     CU(cudaStreamSynchronize(e->stream));
   }
   CU(cudaMemcpyAsync(f.step, step_sizes, sizeof(double) * nd, cudaMemcpyHostToDevice, e->stream));
+  {
+    // 1 - b^(it + 1): in the parameter dtype ((float)b raised in double, rounded once -- jnp.asarray(b1, m.dtype)
+    // ** (i + 1) of the published Adam) and in double for the float64 intercept leaves
+    std::vector<float> bcf(2 * nd);
+    std::vector<double> bcd(2 * nd);
+    for (size_t it = 0; it < nd; ++it) {
+      bcf[2 * it] = 1.0f - (float)std::pow((double)0.9f, (double)(it + 1));
+      bcf[2 * it + 1] = 1.0f - (float)std::pow((double)0.999f, (double)(it + 1));
+      bcd[2 * it] = 1.0 - std::pow(0.9, (double)(it + 1));
+      bcd[2 * it + 1] = 1.0 - std::pow(0.999, (double)(it + 1));
+    }
+    CU(cudaMalloc(&f.bc_f, sizeof(float) * 2 * nd));
+    CU(cudaMalloc(&f.bc_d, sizeof(double) * 2 * nd));
+    CU(cudaMemcpyAsync(f.bc_f, bcf.data(), sizeof(float) * 2 * nd, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(f.bc_d, bcd.data(), sizeof(double) * 2 * nd, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
   CU(cudaMemsetAsync(f.it, 0, sizeof(int), e->stream));
   CU(cudaMemsetAsync(f.m, 0, sizeof(float) * np, e->stream));
   CU(cudaMemsetAsync(f.v, 0, sizeof(float) * np, e->stream));
@@ -2155,6 +2339,8 @@ extern "C" int rfb_fit_begin(rfb_model* m, int max_iters, const double* step_siz
   ua.beta = (float)beta;
   ua.penalise = beta != 0.0 ? 1 : 0;
   ua.step_sizes = f.step;
+  ua.bc_f = f.bc_f;
+  ua.bc_d = f.bc_d;
   ua.cost_train = f.cost_train; ua.cost_dev = f.cost_dev;
   ua.metric_train = f.metric_train; ua.metric_dev = f.metric_dev;
   ua.ring_b = f.ring_b; ua.ring_ic = f.ring_ic;
@@ -2186,6 +2372,7 @@ extern "C" int rfb_fit_begin(rfb_model* m, int max_iters, const double* step_siz
   }
   f.graph = graph;
   CU(cudaGraphInstantiate(&f.exec, f.graph, 0));
+  TRY(plan_small_fit(m));
   f.active = true;
   f.executed = 0;
   f.finished = false;
@@ -2200,11 +2387,27 @@ extern "C" int rfb_fit_run(rfb_model* m, int n_iters) {
   if (n_iters < 0 || f.executed + n_iters > f.max_iters)
     return fail(RFB_ERR_INVALID, "%d more iterations exceed max_iters=%d (executed %d)", n_iters, f.max_iters, f.executed);
   TRY(use_device(m->e));
+  if (f.small && n_iters > 0) {
+    // the whole batch of iterations in one cooperative launch; state stays in the fit's device buffers
+    f.sa.n_iters = n_iters;
+    void* params[] = {(void*)&f.sa};
+    CU(cudaLaunchCooperativeKernel(f.small_fn, dim3(f.small_grid), dim3(kSmallThreads), params, f.small_smem,
+                                   m->e->stream));
+    m->e->launches += 1;
+    f.executed += n_iters;
+    return RFB_OK;
+  }
   for (int k = 0; k < n_iters; ++k) {
     CU(cudaGraphLaunch(f.exec, m->e->stream));
     m->e->launches += f.kernels_per_iter;
   }
   f.executed += n_iters;
+  return RFB_OK;
+}
+
+extern "C" int rfb_fit_is_persistent(rfb_model* m, int* out) {
+  if (!m || !out) return fail(RFB_ERR_INVALID, "NULL argument");
+  *out = (m->fit.active && m->fit.small) ? 1 : 0;
   return RFB_OK;
 }
 

@@ -24,9 +24,30 @@
 // a software-pipelined loop): profiles/sweep_sub_r1_ncu.txt, DESIGN.md section 3.2b.
 #pragma once
 
+#include "project_tc.cuh"
 #include "sweep.cuh"
 
 namespace rfb {
+
+// Tensor memory as accumulator storage for ordinary warps (no MMA involved): tcgen05.ld / tcgen05.st move 16
+// consecutive 32-bit columns of this lane between registers and tensor memory.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ u64_t pack_u32(uint32_t lo, uint32_t hi) {
+  u64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_u32(u64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
 
 constexpr int kSubRows = 8;      // rows per tile: (32 / LPR) row groups x passes
 constexpr int kSubMaxK = 4;      // subunit heads
@@ -71,9 +92,12 @@ __device__ __forceinline__ float transpose_reduce_grp(float (&p)[VN], int lane) 
 // SPEC 0: run-time nonlinearities / distribution; 1: softplus subunits, softplus output, Poisson
 // LPR lanes per row (8 or 16); HOLD: the rows stay in registers from the forward to the backward pass
 // (the stage goes back to the copy engine after the forward loads) instead of being read twice.
-template <int K, int NJ, int LPR, bool HOLD, bool BWD, int SPEC>
+// TM: the gradient accumulators (K x NJ float4 per lane, 80 registers for 4 subunits) live in tensor memory
+// and pass through 16 registers per column chunk during the backward products -- which is what makes HOLD fit.
+template <int K, int NJ, int LPR, bool HOLD, bool BWD, int SPEC, bool TM = false>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const __grid_constant__ SweepArgs a) {
   sweep_stamp(a, 0);
+  constexpr bool TMA = TM && BWD;        // a forward-only sweep has no accumulators
   static_assert(K >= 2 && K <= kSubMaxK && NJ >= 1 && LPR * NJ <= kSubMaxChunks, "shape");
   static_assert(LPR == 8 || LPR == 16, "lanes per row");
   constexpr int RT = kSubRows;
@@ -144,11 +168,36 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
   const bool poisson = SPEC == 1 ? true : (a.distr == RFB_DISTR_POISSON);
   const int out_kind = SPEC == 1 ? RFB_NL_SOFTPLUS : a.out_nl;
 
-  u64_t glo[K][NJ], ghi[K][NJ];
+  u64_t glo[TMA ? 1 : K][TMA ? 1 : NJ], ghi[TMA ? 1 : K][TMA ? 1 : NJ];
 #pragma unroll
-  for (int k = 0; k < K; ++k)
+  for (int k = 0; k < (TMA ? 1 : K); ++k)
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) glo[k][j] = ghi[k][j] = 0ull;
+    for (int j = 0; j < (TMA ? 1 : NJ); ++j) glo[k][j] = ghi[k][j] = 0ull;
+  // tensor memory: warp w touches lanes [32 (w % 4), +32); the warps of a lane quarter take 80 columns each:
+  // column 16 j + 4 k + {0..3} = gradient of chunk slot j, head k
+  __shared__ uint32_t tm_slot;
+  uint32_t tacc = 0;
+  constexpr uint32_t kTmCols = 256;
+  if (TMA) {
+    if (wic == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_slot)), "r"(kTmCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tacc = tm_slot + ((uint32_t)((wic & 3) * 32) << 16) + (uint32_t)((wic >> 2) * 80);
+  }
+  auto zero_tmem = [&]() {
+    uint32_t z[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) z[q] = 0u;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) tmem_st16(tacc + 16u * j, z);
+    tmem_wait_st();
+  };
+  if (TMA) zero_tmem();
   float sc[S_GHEAD];
 #pragma unroll
   for (int k = 0; k < S_GHEAD; ++k) sc[k] = 0.f;
@@ -201,13 +250,24 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
 
   auto flush = [&]() {
     if (BWD) {
+      if (TMA) tmem_wait_st();
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
+      for (int j = 0; j < NJ; ++j) {
+        uint32_t tr[16];
+        if (TMA) {
+          tc::tmem_ld16(tacc + 16u * j, tr);
+          tmem_wait_ld();
+        }
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
+        for (int k = 0; k < K; ++k) {
           float v[4];
-          unpack2(glo[k][j], v[0], v[1]);
-          unpack2(ghi[k][j], v[2], v[3]);
+          if (TMA) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = __uint_as_float(tr[4 * k + q]);
+          } else {
+            unpack2(glo[TMA ? 0 : k][TMA ? 0 : j], v[0], v[1]);
+            unpack2(ghi[TMA ? 0 : k][TMA ? 0 : j], v[2], v[3]);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {               // the row groups hold partial sums of the same columns
 #pragma unroll
@@ -221,9 +281,10 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
             p2[0] = lo;
             p2[1] = hi;
           }
-          glo[k][j] = ghi[k][j] = 0ull;
+          if (!TMA) glo[TMA ? 0 : k][TMA ? 0 : j] = ghi[TMA ? 0 : k][TMA ? 0 : j] = 0ull;
         }
       }
+      if (TMA) zero_tmem();
       float v[4] = {ge.x, ge.y, ge.z, ge.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -398,7 +459,67 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
     if (count_row && !(sm_out && kind_e == RFB_NL_NONE)) sc_e += delta_e;
 
     // backward: G_k += delta_k x, pass by pass (rows from registers, or read again from the stage)
-    if (BWD) {
+    if (TMA) {
+      // accumulators in tensor memory: one column chunk (all heads) at a time through 16 registers, the next
+      // chunk's accumulators in flight meanwhile
+      if (!KEEP) asm volatile("" ::: "memory");
+      u64_t dd[K][NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float d = __shfl_sync(0xffffffffu, delta_k, (lane & ~(LPR - 1)) | (k + KP * p));
+          dd[k][p] = pack2(d, d);
+        }
+        const float de = __shfl_sync(0xffffffffu, delta_e, (lane & ~(LPR - 1)) | (KP * p));
+        ge.x = fmaf(de, xe[p].x, ge.x);
+        ge.y = fmaf(de, xe[p].y, ge.y);
+        ge.z = fmaf(de, xe[p].z, ge.z);
+        ge.w = fmaf(de, xe[p].w, ge.w);
+      }
+      tmem_wait_st();                                  // the previous tile's stores have landed
+      uint32_t rcur[16], rnext[16];
+      tc::tmem_ld16(tacc, rcur);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        tmem_wait_ld();
+        if (j + 1 < NJ) tc::tmem_ld16(tacc + 16u * (j + 1), rnext);
+        u64_t gl[K], gh[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          gl[k] = pack_u32(rcur[4 * k], rcur[4 * k + 1]);
+          gh[k] = pack_u32(rcur[4 * k + 2], rcur[4 * k + 3]);
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          u64_t tl, th;
+          if (KEEP) {
+            tl = xl[p][j];
+            th = xh[p][j];
+          } else {
+            ld2(so + xlane + (uint32_t)(p * NRG) * ldS + jstep * j, tl, th);
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            gl[k] = ffma2(dd[k][p], tl, gl[k]);
+            gh[k] = ffma2(dd[k][p], th, gh[k]);
+          }
+        }
+        uint32_t wv[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) wv[q] = 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          unpack_u32(gl[k], wv[4 * k], wv[4 * k + 1]);
+          unpack_u32(gh[k], wv[4 * k + 2], wv[4 * k + 3]);
+        }
+        tmem_st16(tacc + 16u * j, wv);
+        if (j + 1 < NJ) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) rcur[q] = rnext[q];
+        }
+      }
+    } else if (BWD) {
       if (!KEEP) asm volatile("" ::: "memory");        // read the rows again, do not carry them in registers
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
@@ -420,8 +541,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) {
-            glo[k][j] = ffma2(dd[k], tl, glo[k][j]);
-            ghi[k][j] = ffma2(dd[k], th, ghi[k][j]);
+            glo[TMA ? 0 : k][TMA ? 0 : j] = ffma2(dd[k], tl, glo[TMA ? 0 : k][TMA ? 0 : j]);
+            ghi[TMA ? 0 : k][TMA ? 0 : j] = ffma2(dd[k], th, ghi[TMA ? 0 : k][TMA ? 0 : j]);
           }
         }
         ge.x = fmaf(de, xe[p].x, ge.x);
@@ -472,6 +593,14 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_subunit_kernel(const _
     double s = 0.0;
     for (int wv = 0; wv < wpc; ++wv) s += cta_rows[(size_t)wv * NE + e];
     out[e] = s;
+  }
+  if (TMA) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wic == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_slot), "r"(kTmCols) : "memory");
+    }
   }
   sweep_stamp(a, 1);
 }

@@ -39,6 +39,12 @@ struct UpdateArgs {
   float alpha, beta;    // elastic net, in the parameter dtype like the reference's weak floats
   int penalise;         // beta != 0
   const double* step_sizes;  // [max_iters]
+  // Adam bias corrections per iteration, tabulated by the host at rfb_fit_begin (a double-precision pow
+  // per use was the longest dependent chain of the whole update): bc_f[2 it + {0, 1}] =
+  // 1 - (float)b^(it + 1) in the parameter dtype for the coefficients, bc_d likewise in double for the
+  // float64 intercept leaves
+  const float* bc_f;
+  const double* bc_d;
   double* cost_train;
   double* cost_dev;
   double* metric_train;
@@ -111,9 +117,9 @@ __device__ inline unsigned long long ld_acquire_sys(const unsigned long long* p)
   return v;
 }
 
-__global__ void __launch_bounds__(kUpdateThreads) update_kernel(const UpdateArgs a) {
-  __shared__ double sm[kUpdateThreads / 32];
-  __shared__ float s_bc[2];
+// One iteration's bookkeeping + penalty + Adam by ONE CTA of kUpdateThreads threads.  Shared by the graph
+// path (update_kernel) and the persistent small-model kernel (fit_small.cuh), so both leave identical state.
+__device__ inline void update_body(const UpdateArgs& a, double* sm, float* s_bc) {
   if (a.x.world > 1) {
     // wait until every rank has published this iteration's vector in my buffer, then add the
     // slots in rank order (identical on all ranks)
@@ -170,15 +176,11 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(const UpdateArgs
       cost += (double)pen;
     }
     a.cost_train[it] = cost;
-    // bias corrections: (float)b ** (it + 1) in the parameter dtype
-    s_bc[0] = 1.0f - (float)pow((double)0.9f, (double)(it + 1));
-    s_bc[1] = 1.0f - (float)pow((double)0.999f, (double)(it + 1));
   }
-  __syncthreads();
   const float lr = (float)a.step_sizes[it];
   const float b1 = 0.9f, b2 = 0.999f, c1 = (float)(1.0 - 0.9), c2 = (float)(1.0 - 0.999);
   const float eps = 1e-8f;
-  const float bc1 = s_bc[0], bc2 = s_bc[1];
+  const float bc1 = __ldg(a.bc_f + 2 * it), bc2 = __ldg(a.bc_f + 2 * it + 1);
   const float wl1 = a.beta * a.alpha, wl2 = a.beta * (1.0f - a.alpha);
 
   for (int j = threadIdx.x; j < a.P; j += blockDim.x) {
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(const UpdateArgs
                                 : (double)(float)sc[S_GHEAD + a.head_of[k]];
     const double mk = (1.0 - 0.9) * g + 0.9 * a.mi[k];
     const double vk = (1.0 - 0.999) * (g * g) + 0.999 * a.vi[k];
-    const double mhat = mk / (1.0 - pow(0.9, (double)(it + 1)));
-    const double vhat = vk / (1.0 - pow(0.999, (double)(it + 1)));
+    const double mhat = mk / __ldg(a.bc_d + 2 * it);
+    const double vhat = vk / __ldg(a.bc_d + 2 * it + 1);
     const double xn = a.ic[k] - a.step_sizes[it] * mhat / (sqrt(vhat) + 1e-8);
     a.mi[k] = mk;
     a.vi[k] = vk;
@@ -214,6 +216,12 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(const UpdateArgs
   __syncthreads();
   publish_params(a);
   if (threadIdx.x == 0) *a.it = it + 1;
+}
+
+__global__ void __launch_bounds__(kUpdateThreads) update_kernel(const UpdateArgs a) {
+  __shared__ double sm[kUpdateThreads / 32];
+  __shared__ float s_bc[2];
+  update_body(a, sm, s_bc);
 }
 
 }  // namespace rfb

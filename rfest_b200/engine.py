@@ -434,6 +434,13 @@ class DeviceModel:
         check(self.lib.rfb_fit_run_timed(self.handle, int(n), ms.ctypes.data_as(_lib._dp)))
         return ms
 
+    @property
+    def fit_is_persistent(self):
+        """True when the fit in progress runs as the persistent small-model kernel (csrc/fit_small.cuh)."""
+        v = C.c_int()
+        check(self.lib.rfb_fit_is_persistent(self.handle, C.byref(v)))
+        return bool(v.value)
+
     def fit_sweep_times(self, kind, i0, n):
         """-> ms of the `kind` sweep kernel in iterations [i0, i0 + n), stamped inside the replayed graph."""
         ms = np.zeros(n, dtype=np.float64)

@@ -694,8 +694,11 @@ def test_subunit_sweep_shapes(dims, df, subunits, history, filt_nl, out_nl, dist
     if distr == "gaussian":
         y = (y - y.mean()).astype(np.float32)
     results = {}
-    for variant in (3, 0):        # subunit sweep, row-per-warp kernels
+    # subunit sweep; its stage-pool / tensor-memory variants (15 and 12 consumer warps) on 2 CTAs so that the
+    # pooled stages are reused; row-per-warp kernels
+    for variant in (3, 4, 5, 6, 7, 0):   # 6 / 7: per-warp rings with the accumulators in tensor memory
         Engine.get().set_option("sweep_sub", variant)
+        Engine.get().set_option("sweep_pool_ctas", 2 if variant in (4, 5) else 0)
         try:
             g, o = _pair(distr, out_nl)
             for m in (g, o):
@@ -717,7 +720,8 @@ def test_subunit_sweep_shapes(dims, df, subunits, history, filt_nl, out_nl, dist
             results[variant] = (lg, gg, r)
         finally:
             Engine.get().set_option("sweep_sub", 3)
-        if variant == 3:
+            Engine.get().set_option("sweep_pool_ctas", 0)
+        if variant != 0:
             lo, go = o.value_and_grad(o.p0, "train")
             assert abs(lg - lo) < 1e-6 * abs(lo)
             for name in o.filter_names:
@@ -727,11 +731,61 @@ def test_subunit_sweep_shapes(dims, df, subunits, history, filt_nl, out_nl, dist
             assert abs(gg["intercept"]["global"] - go["intercept"]["global"]) < 2e-5 * max(
                 1.0, abs(go["intercept"]["global"]))
             assert _wrel(r, o.forwardpass(o.p0, "train")) < 1e-6
-    (l3, g3, r3), (l0, g0, r0) = results[3], results[0]
-    assert abs(l3 - l0) < 1e-6 * abs(l0) and _wrel(r3, r0) < 1e-6
-    for name in g3:
-        if name != "intercept":
-            assert np.abs(g3[name] - g0[name]).max() < 2e-5 * np.abs(g0[name]).max()
+    l0, g0, r0 = results[0]
+    for variant in (3, 4, 5, 6, 7):
+        l3, g3, r3 = results[variant]
+        assert abs(l3 - l0) < 1e-6 * abs(l0) and _wrel(r3, r0) < 1e-6
+        for name in g3:
+            if name != "intercept":
+                assert np.abs(g3[name] - g0[name]).max() < 2e-5 * np.abs(g0[name]).max()
+
+
+@pytest.mark.parametrize("subunits,dims,df", [(4, [10, 8, 8], [8, 6, 6]), (3, [8, 6, 6], [5, 4, 4])])
+def test_pooled_subunit_sweep_medium_size(subunits, dims, df):
+    """Enough rows for every consumer warp of every CTA to recycle stages many times and to pass the
+    fp32 -> fp64 flush cadence: the pooled / tensor-memory sweep against the private-ring one (same
+    arithmetic per row, same accumulation cadence: agreement to fp32 summation noise), twice (determinism)."""
+    import torch
+
+    from rfest_b200 import GLM
+    from rfest_b200.engine import Engine
+
+    n = 1_500_011
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    stim = torch.randn((n, dims[1], dims[2]), generator=gen, device="cuda")
+    y = torch.poisson(torch.full((n,), 0.3, device="cuda"), generator=gen)
+    out = {}
+    try:
+        for variant in (3, 4, 4, 5, 6, 6, 7):
+            Engine.get().set_option("sweep_sub", variant)
+            m = GLM(distr="poisson", output_nonlinearity="softplus")
+            m.add_design_matrix(stim, dims=dims, df=df, smooth="cr", filter_nonlinearity="softplus", name="stimulus")
+            m.add_design_matrix(y, dims=[20], df=[8], smooth="cr", shift=1, name="history")
+            m.initialize(num_subunits=subunits, method="random", random_seed=3)
+            for k, name in enumerate(m.filter_names):
+                m.p0[name] = (0.1 * np.random.default_rng(k).standard_normal(m.p0[name].shape)).astype(np.float32)
+            m.alpha, m.beta = 0.5, 0.01
+            m.y["train"] = y[m.burn_in:].cpu().numpy()
+            m._dirty = True
+            out.setdefault(variant, []).append(m.value_and_grad(m.p0, "train"))
+            del m
+    finally:
+        Engine.get().set_option("sweep_sub", 3)
+    (l3, g3), = out[3]
+    (l4, g4), (l4b, g4b) = out[4]
+    (l5, g5), = out[5]
+    (l6, g6), (l6b, g6b) = out[6]
+    (l7, g7), = out[7]
+    assert l4 == l4b and all(np.array_equal(g4[k], g4b[k]) for k in g4 if k != "intercept")   # bit-reproducible
+    assert l6 == l6b and all(np.array_equal(g6[k], g6b[k]) for k in g6 if k != "intercept")
+    for lv, gv in ((l4, g4), (l5, g5), (l6, g6), (l7, g7)):
+        assert abs(lv - l3) < 1e-7 * abs(l3)
+        for name in g3:
+            if name != "intercept":
+                assert np.abs(gv[name] - g3[name]).max() < 1e-5 * np.abs(g3[name]).max()
+            else:
+                for k in g3["intercept"]:
+                    assert abs(gv["intercept"][k] - g3["intercept"][k]) < 1e-5 * max(1.0, abs(g3["intercept"][k]))
 
 
 def test_refit_with_new_response_keeps_plan_and_old_predictions():
@@ -896,3 +950,107 @@ def test_subunit_sweep_tiny_data_sets(n_raw):
     for name in o.filter_names:
         assert np.abs(gg[name] - go[name]).max() < 2e-5 * max(np.abs(go[name]).max(), 1e-12)
     assert _wrel(g.forwardpass(g.p0, "train"), o.forwardpass(o.p0, "train")) < 1e-6
+
+
+# ---- round 2: the persistent small-model kernel (csrc/fit_small.cuh) ------------------------------------
+@pytest.mark.parametrize("distr,out_nl,filt_nl,subunits,history,dev,dims,df", [
+    ("poisson", "softplus", "none", 1, True, True, (25,), (8,)),            # BASELINE config 1 shape
+    ("poisson", "softplus", "none", 1, False, False, (9,), (5,)),
+    ("gaussian", "none", "none", 1, True, True, (8, 3), (4, 3)),
+    ("poisson", "exponential", "tanh", 1, True, True, (8, 3), (4, 3)),       # 2 heads
+    ("poisson", "softplus", "softplus", 2, True, True, (6, 3, 3), (3, 3, 3)),   # 3 heads
+    ("gaussian", "relu", "sigmoid", 4, True, False, (6, 3, 3), (3, 3, 3)),   # 5 heads
+])
+def test_persistent_small_fit_equals_graph_path_and_oracle(distr, out_nl, filt_nl, subunits, history, dev,
+                                                           dims, df):
+    """One cooperative kernel for the whole loop (grid barriers, rows resident in shared memory) must
+    leave the same traces / parameters / predictions as the graph-per-iteration path (summation order
+    differs: ~1e-7) and match the oracle within the north-star tolerances."""
+    from rfest_b200.engine import Engine
+
+    n = 3011
+    stim, y, _ = helpers.lnp_data(n, dims, seed=17, history=history)
+    if distr == "gaussian":
+        y = (y - y.mean()).astype(np.float32)
+    n_tr = 2400 if dev else n
+    eng = Engine.get()
+    fits = {}
+    try:
+        for mode in (2, 0):
+            eng.set_option("fit_persistent", mode)
+            g, o = _pair(distr, out_nl)
+            models = (g, o) if mode == 2 else (g,)
+            for m in models:
+                m.add_design_matrix(stim[:n_tr], dims=list(dims), df=list(df), smooth="cr",
+                                    filter_nonlinearity=filt_nl, name="stimulus")
+                if dev:
+                    m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
+                if history:
+                    m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+                    if dev:
+                        m.add_design_matrix(y[n_tr:], name="history", kind="dev")
+                m.initialize(num_subunits=subunits, method="random", random_seed=3)
+            _same_p0(list(models), icpt=0.02)
+            fit_y = {"train": y[:n_tr]}
+            if dev:
+                fit_y["dev"] = y[n_tr:]
+            for m in models:
+                m.fit(y=fit_y, num_iters=150, alpha=0.5, beta=0.01, metric="corrcoef", step_size=0.02,
+                      tolerance=5, min_iters=100, verbose=0)
+            fits[mode] = g
+            if mode == 2:
+                _compare_fit(g, o, dev)
+                assert g.train_stop == o.train_stop
+    finally:
+        eng.set_option("fit_persistent", 1)
+    a, b = fits[2], fits[0]
+    assert len(a.cost_train) == len(b.cost_train)
+    assert _rel(a.cost_train, b.cost_train) < 2e-6
+    assert np.max(np.abs(a.metric_train - b.metric_train)) < 2e-6
+    if dev:
+        assert _rel(a.cost_dev, b.cost_dev) < 2e-6
+    for name in a.filter_names:
+        assert _wrel(a.all_params[-1][name], b.all_params[-1][name]) < 1e-5
+
+
+def test_persistent_path_is_taken_for_the_readme_recipe_and_not_for_large_data():
+    from rfest_b200 import GLM
+
+    stim, y, _ = helpers.lnp_data(4000, (25,), seed=3)
+    m = GLM(distr="poisson", output_nonlinearity="softplus")
+    m.add_design_matrix(stim, dims=[25], df=[8], smooth="cr", name="stimulus")
+    m.add_design_matrix(y, dims=[20], df=[8], smooth="cr", shift=1, name="history")
+    m.initialize(method="random", random_seed=1)
+    m.alpha, m.beta = 1.0, 0.01
+    m.y["train"] = y[m.burn_in:]
+    m._dirty = True
+    m._sync()
+    m._dm.set_params(*m._flatten(m.p0))
+    m._dm.fit_begin(np.full(10, 0.1), 1.0, 0.01, "corrcoef")
+    assert m._dm.fit_is_persistent
+    launches = m.engine.launch_count
+    m._dm.fit_run(10)
+    m.engine.synchronize()
+    assert m.engine.launch_count - launches == 1              # ten iterations, one kernel
+    first = m._dm.fit_traces(10)[0].copy()
+    m._dm.fit_end()
+    m._dm.set_params(*m._flatten(m.p0))                        # (fit_end keeps the final parameters)
+    m._dm.fit_begin(np.full(10, 0.1), 1.0, 0.01, "corrcoef")   # deterministic: no atomics in the sums
+    m._dm.fit_run(4)
+    m._dm.fit_run(6)                                          # batches continue where the last one stopped
+    assert np.array_equal(first, m._dm.fit_traces(10)[0])
+    m._dm.fit_end()
+
+    rng = np.random.default_rng(0)
+    big = GLM(distr="gaussian")
+    big.add_design_matrix(rng.standard_normal((300000, 6, 5)).astype(np.float32), dims=[4, 6, 5], df=[3, 4, 4],
+                          smooth="cr", name="stimulus")
+    big.initialize(method="random", random_seed=1)
+    big.alpha, big.beta = 1.0, 0.01
+    big.y["train"] = rng.standard_normal(300000).astype(np.float32)[big.burn_in:]
+    big._dirty = True
+    big._sync()
+    big._dm.set_params(*big._flatten(big.p0))
+    big._dm.fit_begin(np.full(3, 0.1), 1.0, 0.01, "mse")
+    assert not big._dm.fit_is_persistent                       # 58 MB of rows: the graph path
+    big._dm.fit_end()
