@@ -6,7 +6,7 @@
 // its slice resident, and an iteration is
 //     sweep over the resident rows (forward, loss, gradient, metric sums; dev: forward only)
 //     -> fixed-order fp64 reduction inside the CTA -> per-CTA partial row in global memory
-//     -> ONE grid barrier -> every CTA adds the partial rows in CTA order and applies the bookkeeping +
+//     -> ONE grid barrier (cooperative groups; a flag-per-CTA exchange is kept as an option) -> every CTA adds the partial rows in CTA order and applies the bookkeeping +
 //     penalty + Adam arithmetic of update_body (update.cuh) to ITS OWN shared-memory copy of the optimiser
 //     state; the copies stay bit-identical, so nobody waits for a broadcast and the next sweep starts at
 //     once.  CTA 0 records the traces and the parameter ring; the partial rows alternate between two
@@ -35,6 +35,8 @@ struct SmallArgs {
   SweepArgs tr, dv;            // dv.n_rows == 0: no dev set
   UpdateArgs ua;               // the fit's state in global memory (read at entry, written back at exit)
   double* part;                // [2 parities][grid][NE + kNumScalars] per-CTA partial sums
+  unsigned long long* flags;   // [grid]: epoch + (iterations of this launch whose partial row is complete)
+  unsigned long long epoch;    // iterations launched before this batch (flags only ever grow)
   int n_iters;
   int rows_tr, rows_dv;        // rows per CTA
   int NE;                      // H * ctot + kNumScalars
@@ -59,9 +61,17 @@ __host__ __device__ inline size_t fit_small_smem_bytes(int rows_tr, int rows_dv,
   return b + 16;
 }
 
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int H>
 __global__ void __launch_bounds__(kSmallThreads, 1) fit_small_kernel(const __grid_constant__ SmallArgs a) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char small_smem[];
   __shared__ double upd_sm[kUpdateThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -238,7 +248,24 @@ __global__ void __launch_bounds__(kSmallThreads, 1) fit_small_kernel(const __gri
       }
       __syncthreads();
     }
-    grid.sync();     // (fences included) the only grid barrier of the iteration: partial rows alternate between two parities
+    // ---- exchange = barrier: every CTA publishes "my partial row of iteration `it` is written" in a flag and
+    // waits for everybody else's; the rows alternate between two parities (a CTA can be at most one iteration
+    // ahead of the slowest one, because it needs that CTA's flag of the previous iteration to get there)
+    // (measured at config 1, 64 CTAs: 12.0 us per iteration with the flags, 9.7 us with the cooperative-groups
+    // grid barrier -- 64 polling threads per CTA cost more than one counter; the flags stay as an option)
+    if (a.flags != nullptr) {
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release_gpu(a.flags + blockIdx.x, (unsigned long long)a.epoch + (unsigned long long)(k + 1));
+      }
+      for (unsigned c = tid; c < gridDim.x; c += kSmallThreads)
+        while (ld_acquire_gpu(a.flags + c) < (unsigned long long)a.epoch + (unsigned long long)(k + 1)) {
+        }
+      __syncthreads();
+    } else {
+      cg::this_grid().sync();
+    }
 
     // ---- every CTA: totals in CTA order, then bookkeeping + penalty + Adam on its own copy of the state ---
     {

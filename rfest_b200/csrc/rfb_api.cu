@@ -280,6 +280,8 @@ struct Fit {
   bool small = false;
   SmallArgs sa{};
   double* small_part = nullptr;
+  unsigned long long* small_flags = nullptr;
+  unsigned long long small_epoch = 0;
   int small_grid = 0;
   size_t small_smem = 0;
   const void* small_fn = nullptr;
@@ -2108,7 +2110,7 @@ static int fit_release(rfb_model* m) {
   if (f.graph) cudaGraphDestroy(f.graph);
   cudaFree(f.step); cudaFree(f.cost_train); cudaFree(f.cost_dev); cudaFree(f.metric_train);
   cudaFree(f.metric_dev); cudaFree(f.ring_b); cudaFree(f.ring_ic); cudaFree(f.it);
-  cudaFree(f.m); cudaFree(f.v); cudaFree(f.mi); cudaFree(f.vi); cudaFree(f.fin); cudaFree(f.stamps); cudaFree(f.small_part); cudaFree(f.bc_f); cudaFree(f.bc_d);
+  cudaFree(f.m); cudaFree(f.v); cudaFree(f.mi); cudaFree(f.vi); cudaFree(f.fin); cudaFree(f.stamps); cudaFree(f.small_part); cudaFree(f.small_flags); cudaFree(f.bc_f); cudaFree(f.bc_d);
   f = Fit();
   return RFB_OK;
 }
@@ -2199,7 +2201,7 @@ static int plan_small_fit(rfb_model* m) {
   const DataSet& dev = m->data[RFB_KIND_DEV];
   const int64_t n_dev = f.has_dev ? dev.n : 0;
   const double bytes = 4.0 * (double)(tr.n + n_dev) * (p.ctot + 1);
-  if (bytes > 8.0 * 1024 * 1024 && e->fit_persistent < 2) return RFB_OK;     // 2: force (tests)
+  if (bytes > 8.0 * 1024 * 1024 && e->fit_persistent < 2) return RFB_OK;     // 2, 3: whenever the data fit (tests)
   const void* fn = p.Ht == 1 ? (const void*)fit_small_kernel<1> : p.Ht == 2 ? (const void*)fit_small_kernel<2>
                  : p.Ht == 3 ? (const void*)fit_small_kernel<3> : (const void*)fit_small_kernel<5>;
     int lpr = 1;
@@ -2219,6 +2221,9 @@ static int plan_small_fit(rfb_model* m) {
   const size_t row = (size_t)p.NE + kNumScalars;
   CU(cudaMalloc(&f.small_part, sizeof(double) * 2 * row * (size_t)grid));
   CU(cudaMemsetAsync(f.small_part, 0, sizeof(double) * 2 * row * (size_t)grid, e->stream));
+  CU(cudaMalloc(&f.small_flags, sizeof(unsigned long long) * (size_t)grid));
+  CU(cudaMemsetAsync(f.small_flags, 0, sizeof(unsigned long long) * (size_t)grid, e->stream));
+  f.small_epoch = 0;
   SmallArgs& sa = f.sa;
   sa = SmallArgs{};
   sa.tr = make_sweep_args(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), -1, nullptr);
@@ -2231,6 +2236,7 @@ static int plan_small_fit(rfb_model* m) {
   sa.ua.sum_lo = 0;
   sa.ua.sum_hi = 0;
   sa.part = f.small_part;
+  sa.flags = e->fit_persistent == 3 ? f.small_flags : nullptr;   // 3: flag exchange instead of the grid barrier
   sa.rows_tr = rows_tr;
   sa.rows_dv = rows_dv;
   sa.NE = p.NE;
@@ -2390,6 +2396,8 @@ extern "C" int rfb_fit_run(rfb_model* m, int n_iters) {
   if (f.small && n_iters > 0) {
     // the whole batch of iterations in one cooperative launch; state stays in the fit's device buffers
     f.sa.n_iters = n_iters;
+    f.sa.epoch = f.small_epoch;
+    f.small_epoch += (unsigned long long)n_iters;
     void* params[] = {(void*)&f.sa};
     CU(cudaLaunchCooperativeKernel(f.small_fn, dim3(f.small_grid), dim3(kSmallThreads), params, f.small_smem,
                                    m->e->stream));
