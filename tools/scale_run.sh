@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for g in 1 2 4 8; do
   [ $g -gt $N ] && break
   if [ $g -eq 1 ]; then
-    python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${g}.json 2> gpurun_out/scale_${g}.err
+    python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/scale_${g}.json 2> gpurun_out/scale_${g}.err
   else
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port $((29600 + g)) \
       bench.py --gpus $g --steps 20 --warmup 3 > gpurun_out/scale_${g}.json 2> gpurun_out/scale_${g}.err

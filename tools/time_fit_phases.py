@@ -41,7 +41,7 @@ for rep in range(3):
 
 acc = collections.OrderedDict()
 dm = m._dm
-for name in ["clear_filters", "add_filter", "set_data", "set_params", "fit_begin", "fit_run", "fit_finish",
+for name in ["clear_filters", "add_filter", "set_data", "set_y", "set_params", "fit_begin", "fit_run", "fit_finish",
              "fit_traces", "fit_params_all", "fit_predictions_device", "fit_end"]:
     fn = getattr(dm, name)
 
