@@ -119,28 +119,83 @@ struct BandArgs {
   float* pred;                        // [n_rows] each
   float* upper;
   float* lower;
+  // 'softmax' (a normalisation over ALL samples, _glm.py:134-140) applies to each of the three lines on its
+  // own, as the reference's three fnl calls do (_glm.py:1187-1219):
+  //   mode 1: block partials of sum exp over the three drives of filter `which`
+  //   mode 2: block partials of sum exp over the three output drives (filters already normalised)
+  //   mode 0: write the three lines
+  int mode, which;
+  const float* fscale;                // [3 n_filters] device: 1 / sum for softmax filters
+  const float* oscale;                // [3] device: 1 / sum for a softmax output
+  double* part;                       // [3 gridDim.x] (modes 1, 2)
 };
 
+constexpr int kBandBlocks = 592;
+
 __global__ void __launch_bounds__(256) band_combine_kernel(const BandArgs a) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.n_rows) return;
-  float mid = 0.f, up = 0.f, lo = 0.f, f, d;
-  for (int i = 0; i < a.n_filters; ++i) {
-    const float base = a.lin[i][t] + a.icpt[i];
-    const float s2 = a.se[i] ? 2.0f * a.se[i][t] : 0.f;
-    nl_eval(a.nl[i], base, f, d);
-    mid += f;
-    nl_eval(a.nl[i], base + s2, f, d);
-    up += f;
-    nl_eval(a.nl[i], base - s2, f, d);
-    lo += f;
+  double s[3] = {0.0, 0.0, 0.0};
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.n_rows;
+       t += (long long)gridDim.x * blockDim.x) {
+    float line[3] = {0.f, 0.f, 0.f}, f, d;
+    if (a.mode == 1) {
+      const int i = a.which;
+      const float base = a.lin[i][t] + a.icpt[i];
+      const float s2 = a.se[i] ? 2.0f * a.se[i][t] : 0.f;
+      s[0] += (double)expf(base);
+      s[1] += (double)expf(base + s2);
+      s[2] += (double)expf(base - s2);
+      continue;
+    }
+    for (int i = 0; i < a.n_filters; ++i) {
+      const float base = a.lin[i][t] + a.icpt[i];
+      const float s2 = a.se[i] ? 2.0f * a.se[i][t] : 0.f;
+      const bool smx = a.nl[i] == RFB_NL_SOFTMAX;
+      nl_eval(a.nl[i], base, f, d);
+      line[0] += smx ? f * __ldg(a.fscale + 3 * i) : f;
+      nl_eval(a.nl[i], base + s2, f, d);
+      line[1] += smx ? f * __ldg(a.fscale + 3 * i + 1) : f;
+      nl_eval(a.nl[i], base - s2, f, d);
+      line[2] += smx ? f * __ldg(a.fscale + 3 * i + 2) : f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      nl_eval(a.out_nl, line[k] + a.glob_icpt, f, d);
+      if (a.mode == 2) s[k] += (double)f;
+      else if (a.out_nl == RFB_NL_SOFTMAX) line[k] = f * __ldg(a.oscale + k);
+      else line[k] = f;
+    }
+    if (a.mode == 0) {
+      a.pred[t] = line[0];
+      a.upper[t] = line[1];
+      a.lower[t] = line[2];
+    }
   }
-  nl_eval(a.out_nl, mid + a.glob_icpt, f, d);
-  a.pred[t] = f;
-  nl_eval(a.out_nl, up + a.glob_icpt, f, d);
-  a.upper[t] = f;
-  nl_eval(a.out_nl, lo + a.glob_icpt, f, d);
-  a.lower[t] = f;
+  if (a.mode != 0) {
+    __shared__ double sh[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double v = warp_sum_f64(s[k]);
+      if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += sh[threadIdx.x][w];
+      a.part[3 * blockIdx.x + threadIdx.x] = v;
+    }
+  }
+}
+
+// fixed-order sum of the block partials -> sums[3]
+__global__ void band_sum_kernel(const double* part, int n_part, double* sums) {
+  if (blockIdx.x == 0 && threadIdx.x < 3) {
+    double v = 0.0;
+    for (int k = 0; k < n_part; ++k) v += part[3 * k + threadIdx.x];
+    sums[threadIdx.x] = v;
+  }
+}
+__global__ void band_scale_kernel(const double* sums, float* scale) {
+  if (blockIdx.x == 0 && threadIdx.x < 3) scale[threadIdx.x] = (float)(1.0 / sums[threadIdx.x]);
 }
 
 }  // namespace rfb

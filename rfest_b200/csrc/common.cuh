@@ -50,6 +50,10 @@ struct SweepArgs {
   int flush_tiles;                  // fp32 -> fp64 flush cadence, in tiles
   int n_stages;                     // staged variant: depth of each warp's copy ring
   const float* softmax;             // out_nl == RFB_NL_SOFTMAX: {1 / Z, D} on the device (see softmax_scale)
+  // 'softmax' as a FILTER nonlinearity (head_softmax_fix in sweep.cuh): head_scale[h] = 1 / Z_h on the device;
+  // prep != 0 marks the preparatory sweep that produces Z_h = sum exp(a_h) and E_h = sum exp(a_h) x
+  const float* head_scale;
+  int prep;
   // subunit sweep (sweep_sub.cuh): K heads share the block of slot `sub_slot`; at most one other head
   int sub_slot;
   int sub_head[4];                  // head index (accumulator layout) of every subunit

@@ -232,6 +232,7 @@ struct Plan {
   int Ht = 0;  // template head count (>= H)
   int NCH = 0; // template chunks per lane
   int RB = 0;
+  int n_smx = 0;          // heads whose filter nonlinearity is 'softmax' (a normalisation over all samples)
   bool generic = false;   // shape outside the register-resident kernels: generic fallback sweep
   int n_slots = 0;
   int slot_chunk0[kMaxSlots + 1] = {};
@@ -304,6 +305,10 @@ struct rfb_model {
   double* sm_scal[3] = {};
   double* sm_part[3] = {};
   float* sm_f[3] = {};
+  // softmax filter heads: per data set the summed vector of the preparatory sweep and 1 / Z_h
+  double* smx_fin[3] = {};
+  int smx_fin_n[3] = {};
+  float* smx_scale[3] = {};
   Fit fit;
 };
 
@@ -440,9 +445,12 @@ static int build_plan(rfb_model* m) {
     p.RB = kGenRB;
   }
   p.head_nl.assign(p.Ht, RFB_NL_NONE);
-  for (int h = 0; h < p.H; ++h) p.head_nl[h] = heads[h].nl;
+  for (int h = 0; h < p.H; ++h) {
+    p.head_nl[h] = heads[h].nl;
+    if (heads[h].nl == RFB_NL_SOFTMAX) ++p.n_smx;
+  }
   p.NE = sweep_num_entries(p.Ht, p.n_chunks);
-  if (!p.generic && p.H >= 2) {
+  if (!p.generic && p.H >= 2 && p.n_smx == 0) {   // (softmax heads need the run-time-kind row-per-warp kernels)
     for (int s = 0; s < n_slots && !p.sub.ok; ++s) {
       SubPlan sp;
       int others = 0;
@@ -797,7 +805,7 @@ static SweepArgs make_sweep_args(const rfb_model* m, int kind, const ParamSet& p
 }
 
 static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* head_nl, bool bwd,
-                        float* r_out, int out_nl_override = -1, const float* softmax = nullptr) {
+                        float* r_out, int out_nl_override = -1, const float* softmax = nullptr, int prep = 0) {
   const Plan& p = m->plan;
   rfb_engine* e = m->e;
   int RB = p.RB;
@@ -820,6 +828,9 @@ static int launch_sweep(rfb_model* m, int kind, const ParamSet& ps, const int* h
   a.warp_acc = sb.warp_acc;
   a.cta_part = sb.cta_part;
   a.r_out = r_out;
+  a.head_scale = p.n_smx ? m->smx_scale[kind] : nullptr;
+  a.prep = prep;
+  if (p.n_smx && !a.head_scale) return fail(RFB_ERR_STATE, "softmax filter heads without their normalisers");
   a.flush_tiles = std::max(1, 256 / RB);
   a.n_stages = sb.stages;
   if (m->fit.stamp_now && m->fit.stamps && kind <= RFB_KIND_DEV) {
@@ -904,6 +915,58 @@ static int softmax_prepare(rfb_model* m, int kind, const ParamSet& ps, const int
   }
   softmax_finish_kernel<<<1, 32, 0, e->stream>>>(Z, want_d ? D : nullptr, m->sm_f[kind]);
   e->launches++;
+  CU(cudaGetLastError());
+  return RFB_OK;
+}
+
+// ---- 'softmax' as a filter nonlinearity (head_softmax_fix in sweep.cuh, smx_*_kernel in softmax.cuh) ---------
+static SmxHeads smx_heads(const Plan& p, const int* head_nl) {
+  SmxHeads hs{};
+  hs.n_heads = p.Ht;
+  for (int h = 0; h < p.Ht; ++h) hs.is_smx[h] = head_nl[h] == RFB_NL_SOFTMAX;
+  return hs;
+}
+// not capturable (allocation): the fit calls this before it captures the iteration
+static int ensure_smx_buffers(rfb_model* m, int kind) {
+  const Plan& p = m->plan;
+  if (!p.n_smx) return RFB_OK;
+  if (m->smx_fin[kind] && m->smx_fin_n[kind] != p.NE) {
+    CU(cudaFree(m->smx_fin[kind]));
+    m->smx_fin[kind] = nullptr;
+  }
+  if (!m->smx_fin[kind]) {
+    CU(cudaMalloc(&m->smx_fin[kind], sizeof(double) * p.NE));
+    m->smx_fin_n[kind] = p.NE;
+  }
+  if (!m->smx_scale[kind]) CU(cudaMalloc(&m->smx_scale[kind], sizeof(float) * kMaxHeads));
+  return RFB_OK;
+}
+// Enqueue the preparatory sweep at parameters `ps`: afterwards m->smx_scale[kind] holds 1 / Z_h and (want_grad)
+// m->smx_fin[kind] the vectors E_h that smx_fix needs.
+static int smx_prepare(rfb_model* m, int kind, const ParamSet& ps, const int* head_nl, bool want_grad) {
+  const Plan& p = m->plan;
+  if (!p.n_smx) return RFB_OK;
+  bool any = false;
+  for (int h = 0; h < p.Ht; ++h) any = any || head_nl[h] == RFB_NL_SOFTMAX;
+  const int tail = p.Ht * p.ctot;
+  if (any) {
+    // (the output stage is irrelevant here -- delta is forced to 1 -- so it runs as the identity)
+    TRY(launch_sweep(m, kind, ps, head_nl, want_grad, nullptr, RFB_NL_NONE, nullptr, 1));
+    const int lo = want_grad ? 0 : tail;
+    TRY(launch_reduce(m, kind, lo, p.NE - lo, m->smx_fin[kind] + lo, -1, 0, 0, nullptr));
+    TRY(allreduce_device_f64(m->e, m->smx_fin[kind] + lo, (size_t)(p.NE - lo)));
+  }
+  smx_finish_kernel<<<1, 32, 0, m->e->stream>>>(m->smx_fin[kind], tail, smx_heads(p, head_nl), m->smx_scale[kind]);
+  m->e->launches++;
+  CU(cudaGetLastError());
+  return RFB_OK;
+}
+// after the ordinary sweep's sums are complete (all ranks): the cross-sample term of the softmax Jacobian
+static int smx_fix(rfb_model* m, int kind, const int* head_nl, double* fin) {
+  const Plan& p = m->plan;
+  if (!p.n_smx) return RFB_OK;
+  smx_fix_kernel<<<1, 256, 0, m->e->stream>>>(fin, m->smx_fin[kind], p.ctot, p.Ht * p.ctot, smx_heads(p, head_nl));
+  m->e->launches++;
   CU(cudaGetLastError());
   return RFB_OK;
 }
@@ -1620,6 +1683,8 @@ extern "C" int rfb_model_destroy(rfb_model* m) {
     cudaFree(m->sm_scal[k]);
     cudaFree(m->sm_part[k]);
     cudaFree(m->sm_f[k]);
+    cudaFree(m->smx_fin[k]);
+    cudaFree(m->smx_scale[k]);
   }
   delete m;
   return RFB_OK;
@@ -1640,9 +1705,8 @@ extern "C" int rfb_model_clear_filters(rfb_model* m) {
 extern "C" int rfb_model_add_filter(rfb_model* m, int slot, int filter_nl, int n_coef) {
   if (!m) return fail(RFB_ERR_INVALID, "model is NULL");
   if (slot < 0 || slot >= kMaxSlots) return fail(RFB_ERR_UNSUPPORTED, "slot %d out of range (max %d)", slot, kMaxSlots);
-  if (filter_nl == RFB_NL_SOFTMAX)
-    return fail(RFB_ERR_UNSUPPORTED, "softmax is available as the output nonlinearity only");
-  if (!valid_nl(filter_nl)) return fail(RFB_ERR_UNSUPPORTED, "unknown filter nonlinearity %d", filter_nl);
+  if (!valid_nl(filter_nl) && filter_nl != RFB_NL_SOFTMAX)
+    return fail(RFB_ERR_UNSUPPORTED, "unknown filter nonlinearity %d", filter_nl);
   if (n_coef < 1) return fail(RFB_ERR_INVALID, "filter needs at least one coefficient");
   if (m->fit.active) return fail(RFB_ERR_STATE, "cannot add filters during a fit");
   m->filters.push_back({slot, filter_nl, n_coef});
@@ -1839,6 +1903,8 @@ static int eval_impl(rfb_model* m, int kind, const float* b, const double* inter
   const bool want_grad = grad_b != nullptr || grad_ic != nullptr;
   if (want_grad && !ds.has_y) return fail(RFB_ERR_STATE, "a gradient needs the response of kind %d", kind);
   const float* d_sm = nullptr;
+  TRY(ensure_smx_buffers(m, kind));
+  TRY(smx_prepare(m, kind, m->tmp, head_nl.data(), want_grad));
   if (m->out_nl == RFB_NL_SOFTMAX) {
     TRY(ensure_softmax_buffers(m, kind));
     if (d_r) d_r = ds.r_buf;
@@ -1852,6 +1918,7 @@ static int eval_impl(rfb_model* m, int kind, const float* b, const double* inter
   if (want_grad) {
     TRY(launch_reduce(m, kind, 0, p.NE, m->fin_eval, -1, 0, 0, nullptr));
     TRY(allreduce_device_f64(e, m->fin_eval, p.NE));
+    TRY(smx_fix(m, kind, head_nl.data(), m->fin_eval));
     fin.resize(p.NE);
     CU(cudaMemcpyAsync(fin.data(), m->fin_eval, sizeof(double) * p.NE, cudaMemcpyDeviceToHost, e->stream));
   } else {
@@ -2039,7 +2106,8 @@ extern "C" int rfb_model_response_band(rfb_model* m, int kind, const float* b, c
   size_t v_floats = 0;
   for (int f = 0; f < p.F; ++f) v_floats += (size_t)m->filters[f].n_coef * m->filters[f].n_coef;
   float *d_rows = nullptr, *d_small = nullptr, *d_out = nullptr;
-  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_small); cudaFree(d_out); };
+  void* d_smx = nullptr;
+  auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_small); cudaFree(d_out); cudaFree(d_smx); };
   if (cudaMalloc(&d_rows, sizeof(float) * std::max<size_t>(n, 1) * 2 * p.F) != cudaSuccess) {
     cudaGetLastError();
     return fail(RFB_ERR_CUDA, "out of device memory");
@@ -2085,10 +2153,40 @@ extern "C" int rfb_model_response_band(rfb_model* m, int kind, const float* b, c
   ba.pred = on_device ? pred : d_out;
   ba.upper = on_device ? upper : d_out + n;
   ba.lower = on_device ? lower : d_out + 2 * n;
-  if (ds.n > 0) {
-    band_combine_kernel<<<(unsigned)((ds.n + 255) / 256), 256, 0, e->stream>>>(ba);
-    e->launches++;
+  const int band_grid = (int)std::max<int64_t>(1, std::min<int64_t>(kBandBlocks, (ds.n + 255) / 256));
+  // softmax lines are normalised over all samples (and ranks): sums first, one filter / the output at a time
+  bool any_smx = m->out_nl == RFB_NL_SOFTMAX;
+  for (int i = 0; i < ba.n_filters; ++i) any_smx = any_smx || ba.nl[i] == RFB_NL_SOFTMAX;
+  if (any_smx) {
+    if (cudaMalloc(&d_smx, sizeof(double) * (3 * kBandBlocks + 4) + sizeof(float) * 3 * (ba.n_filters + 1)) != cudaSuccess) {
+      cleanup();
+      return fail(RFB_ERR_CUDA, "out of device memory");
+    }
+    double* d_part = (double*)d_smx;
+    double* d_sums = d_part + 3 * kBandBlocks;
+    float* d_scale = (float*)(d_sums + 4);
+    ba.part = d_part;
+    ba.fscale = d_scale;
+    ba.oscale = d_scale + 3 * ba.n_filters;
+    auto normaliser = [&](int mode, int which, float* out) -> int {
+      ba.mode = mode;
+      ba.which = which;
+      band_combine_kernel<<<band_grid, 256, 0, e->stream>>>(ba);
+      band_sum_kernel<<<1, 32, 0, e->stream>>>(d_part, band_grid, d_sums);
+      int rc = allreduce_device_f64(e, d_sums, 3);
+      band_scale_kernel<<<1, 32, 0, e->stream>>>(d_sums, out);
+      e->launches += 3;
+      return rc;
+    };
+    int rc = RFB_OK;
+    for (int i = 0; i < ba.n_filters && rc == RFB_OK; ++i)
+      if (ba.nl[i] == RFB_NL_SOFTMAX) rc = normaliser(1, i, d_scale + 3 * i);
+    if (rc == RFB_OK && m->out_nl == RFB_NL_SOFTMAX) rc = normaliser(2, 0, d_scale + 3 * ba.n_filters);
+    if (rc != RFB_OK) { cudaStreamSynchronize(e->stream); cleanup(); return rc; }
+    ba.mode = 0;
   }
+  band_combine_kernel<<<band_grid, 256, 0, e->stream>>>(ba);
+  e->launches++;
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess && !on_device) {
     cudaMemcpyAsync(pred, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream);
@@ -2133,6 +2231,7 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   rfb_engine* e = m->e;
   const bool softmax = m->out_nl == RFB_NL_SOFTMAX;
   if (ev) CU(cudaEventRecord(ev[0], e->stream));
+  TRY(smx_prepare(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only));
   if (softmax) TRY(softmax_prepare(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only));
   f.stamp_now = true;
   int rc_sweep = launch_sweep(m, RFB_KIND_TRAIN, m->cur, p.head_nl.data(), !final_only, r_train, -1,
@@ -2141,6 +2240,7 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   TRY(rc_sweep);
   if (ev) CU(cudaEventRecord(ev[1], e->stream));
   if (f.has_dev) {
+    TRY(smx_prepare(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false));
     if (softmax) TRY(softmax_prepare(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false));
     f.stamp_now = true;
     rc_sweep = launch_sweep(m, RFB_KIND_DEV, m->cur, p.head_nl.data(), false, r_dev, -1,
@@ -2150,7 +2250,9 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
   }
   if (ev) CU(cudaEventRecord(ev[2], e->stream));
   const int tail = p.Ht * p.ctot;
-  const bool xchg = e->comm && e->use_xchg && e->xchg_ready && (long long)p.NE + kNumScalars <= e->xchg_cap;
+  // (softmax filter heads correct the summed vector between the exchange and the update: unfused path)
+  const bool xchg = e->comm && e->use_xchg && e->xchg_ready && (long long)p.NE + kNumScalars <= e->xchg_cap &&
+                    p.n_smx == 0;
   const int lo = final_only ? tail : 0;
   const int n_train = p.NE - lo;
   long long sum_lo = lo, sum_hi = (long long)p.NE + (f.has_dev ? kNumScalars : 0);
@@ -2176,6 +2278,7 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
     TRY(launch_reduce(m, RFB_KIND_TRAIN, lo, n_train, f.fin + lo, f.has_dev ? RFB_KIND_DEV : -1, tail,
                       kNumScalars, f.fin + p.NE));
     TRY(allreduce_device_f64(e, f.fin + lo, (size_t)(sum_hi - lo)));
+    if (!final_only) TRY(smx_fix(m, RFB_KIND_TRAIN, p.head_nl.data(), f.fin));
   }
   if (ev) CU(cudaEventRecord(ev[3], e->stream));
   UpdateArgs ua = f.ua;
@@ -2199,7 +2302,7 @@ static int plan_small_fit(rfb_model* m) {
   const Plan& p = m->plan;
   rfb_engine* e = m->e;
   f.small = false;
-  if (!e->fit_persistent || e->world > 1 || m->out_nl == RFB_NL_SOFTMAX || p.generic) return RFB_OK;
+  if (!e->fit_persistent || e->world > 1 || m->out_nl == RFB_NL_SOFTMAX || p.generic || p.n_smx) return RFB_OK;
   if (p.F > 100 || p.n_chunks > kSmallMaxChunks || !(p.Ht == 1 || p.Ht == 2 || p.Ht == 3 || p.Ht == 5)) return RFB_OK;
   const DataSet& tr = m->data[RFB_KIND_TRAIN];
   const DataSet& dev = m->data[RFB_KIND_DEV];
@@ -2365,6 +2468,8 @@ extern "C" int rfb_fit_begin(rfb_model* m, int max_iters, const double* step_siz
     TRY(ensure_softmax_buffers(m, RFB_KIND_TRAIN));
     if (f.has_dev) TRY(ensure_softmax_buffers(m, RFB_KIND_DEV));
   }
+  TRY(ensure_smx_buffers(m, RFB_KIND_TRAIN));
+  if (f.has_dev) TRY(ensure_smx_buffers(m, RFB_KIND_DEV));
   CU(cudaStreamSynchronize(e->stream));
 
   const int64_t l0 = e->launches;

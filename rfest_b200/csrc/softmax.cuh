@@ -115,4 +115,31 @@ __global__ void softmax_finish_kernel(const double* Zp, const double* Dp, float*
   }
 }
 
+// ---- 'softmax' as a filter nonlinearity (head_softmax_fix in sweep.cuh) ---------------------------
+struct SmxHeads {
+  int n_heads;
+  int is_smx[kMaxHeads];
+};
+
+// prep[tail + S_GHEAD + h] = Z_h (all ranks) -> scale[h] = 1 / Z_h in the sweep's arithmetic type
+__global__ void smx_finish_kernel(const double* prep, int tail, SmxHeads hs, float* scale) {
+  const int h = threadIdx.x;
+  if (blockIdx.x == 0 && h < hs.n_heads) scale[h] = hs.is_smx[h] ? (float)(1.0 / prep[tail + S_GHEAD + h]) : 1.f;
+}
+
+// fin: the summed gradient vector of the ordinary sweep, prep: that of the preparatory sweep.  For every softmax
+// head  G_h -= D_h E_h / Z_h  with D_h = fin[tail + S_GHEAD + h]; its intercept gradient is exactly 0 (a shift of
+// a_h does not change the head's output), reported as such rather than as rounding noise.
+__global__ void __launch_bounds__(256)
+smx_fix_kernel(double* fin, const double* prep, int ctot, int tail, SmxHeads hs) {
+  for (int h = 0; h < hs.n_heads; ++h) {
+    if (!hs.is_smx[h]) continue;
+    const double k = fin[tail + S_GHEAD + h] / prep[tail + S_GHEAD + h];
+    for (int c = threadIdx.x; c < ctot; c += blockDim.x) fin[(size_t)h * ctot + c] -= k * prep[(size_t)h * ctot + c];
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < hs.n_heads; h += blockDim.x)
+    if (hs.is_smx[h]) fin[tail + S_GHEAD + h] = 0.0;
+}
+
 }  // namespace rfb

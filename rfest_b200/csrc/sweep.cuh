@@ -158,6 +158,20 @@ __device__ __forceinline__ float softmax_delta(const SweepArgs& a, int out_kind,
   return rowok ? r * (dldr - __ldg(a.softmax + 1)) : 0.f;
 }
 
+// 'softmax' as a FILTER nonlinearity (GLM.fnl via forwardpass, _glm.py:134-140,561-565): head h's output is
+// o_t = exp(a_t) / Z_h with Z_h = sum_s exp(a_s) over every sample of the data set (all ranks), so
+//   dL/da_s = o_s (g_s - D_h),  g_s = dL/do_s = delta_s,  D_h = sum_t g_t o_t
+// and the coefficient gradient is  sum_s delta_s o_s x_s  -  D_h * (sum_s exp(a_s) x_s) / Z_h.
+// A preparatory sweep (a.prep: delta == 1, heads unscaled) yields Z_h in the head-intercept slot and
+// E_h = sum exp(a) x in the gradient rows; the ordinary sweep then runs with phi = phi' = exp(a) / Z_h, which
+// puts D_h into the head-intercept slot, and smx_fix_kernel (softmax.cuh) subtracts D_h E_h / Z_h.
+__device__ __forceinline__ void head_softmax_fix(const SweepArgs& a, int kind, int h, float& f, float& d) {
+  if (kind == RFB_NL_SOFTMAX) {
+    if (!a.prep) f *= __ldg(a.head_scale + h);
+    d = f;
+  }
+}
+
 // ---- per-row epilogue shared by both variants: nonlinearities, loss terms, delta -------------------
 // `tot[h]` = this lane's row's dot products.  Fills r, delta-scaled head derivatives dh[] and adds
 // the row's terms to the fp32 scalar partials when `count`.
@@ -178,6 +192,7 @@ __device__ __forceinline__ void row_epilogue(const SweepArgs& a, const float (&t
   for (int h = 0; h < H; ++h) {
     float f;
     nl_eval(SPEC == 0 ? a.head_nl[h] : RFB_NL_NONE, tot[h] + hic[h], f, dh[h]);
+    if (SPEC == 0) head_softmax_fix(a, a.head_nl[h], h, f, dh[h]);
     u += f;
   }
   u += gic;
@@ -201,6 +216,7 @@ __device__ __forceinline__ void row_epilogue(const SweepArgs& a, const float (&t
   }
   float delta = (dldr == 0.f || !rowok) ? 0.f : dldr * dr;
   if (SPEC == 0) delta = softmax_delta(a, out_kind, delta, r, dldr, rowok);
+  if (SPEC == 0 && a.prep) delta = rowok ? 1.f : 0.f;
   if (count) {
     sc[S_LOSS_A] += la;
     sc[S_LOSS_B] += lb;
@@ -232,6 +248,7 @@ __device__ __forceinline__ void multihead_epilogue(const SweepArgs& a, float tot
                                                    float (&sc)[kNumScalars], float& sc_head) {
   float f, dphi;
   nl_eval(kind_lane, tot + hic_lane, f, dphi);
+  head_softmax_fix(a, kind_lane, min(lane / RB, H - 1), f, dphi);
   float u = lane_valid ? f : 0.f;
 #pragma unroll
   for (int m = RB; m < VP; m <<= 1) u += __shfl_xor_sync(0xffffffffu, u, m);
@@ -254,7 +271,8 @@ __device__ __forceinline__ void multihead_epilogue(const SweepArgs& a, float tot
     lb = 0.f;
     dldr = -err * a.two_over_n;
   }
-  const float delta = softmax_delta(a, a.out_nl, (dldr == 0.f || !rowok) ? 0.f : dldr * dr, r, dldr, rowok);
+  float delta = softmax_delta(a, a.out_nl, (dldr == 0.f || !rowok) ? 0.f : dldr * dr, r, dldr, rowok);
+  if (a.prep) delta = rowok ? 1.f : 0.f;
   if (rowok && lane < RB) {
     sc[S_LOSS_A] += la;
     sc[S_LOSS_B] += lb;
@@ -866,6 +884,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
       }
       float f, dphi;
       nl_eval(kind_lane, mine + hic_lane, f, dphi);
+      head_softmax_fix(a, kind_lane, min(lane, H - 1), f, dphi);
       float u = lane < H ? f : 0.f;
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) u += __shfl_xor_sync(0xffffffffu, u, m);
@@ -891,7 +910,8 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_generic_kernel(const __gr
         lb = 0.f;
         dldr = -err * a.two_over_n;
       }
-      const float delta = softmax_delta(a, a.out_nl, (dldr == 0.f || !rowok) ? 0.f : dldr * dr, rr, dldr, rowok);
+      float delta = softmax_delta(a, a.out_nl, (dldr == 0.f || !rowok) ? 0.f : dldr * dr, rr, dldr, rowok);
+      if (a.prep) delta = rowok ? 1.f : 0.f;
       if (rowok && lane == 0) {
         sc[S_LOSS_A] += la; sc[S_LOSS_B] += lb; sc[S_R] += rr; sc[S_RR] += rr * rr;
         sc[S_YR] += yv * rr; sc[S_SQERR] += err * err;

@@ -175,9 +175,6 @@ class GLM:
         if filter_nonlinearity not in _lib.NL:
             raise NotImplementedError(
                 f"Input filter nonlinearity `{filter_nonlinearity}` is not supported.")
-        if filter_nonlinearity == "softmax":
-            raise NotImplementedError("`softmax` (a normalisation over all samples) is available as the "
-                                      "output nonlinearity only.")
         streamed = _is_row_source(X)
         if streamed and global_rows is not None:
             raise ValueError("a row source already addresses the whole recording; drop `global_rows`")

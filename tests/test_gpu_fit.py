@@ -472,7 +472,9 @@ def test_filter_covariance_matches_oracle(distr, out_nl, filt_nl):
 
 @pytest.mark.parametrize("distr,out_nl,filt_nl,subunits", [("poisson", "softplus", "none", 1),
                                                           ("gaussian", "none", "none", 1),
-                                                          ("poisson", "exponential", "softplus", 2)])
+                                                          ("poisson", "exponential", "softplus", 2),
+                                                          ("poisson", "softmax", "none", 1),
+                                                          ("poisson", "softplus", "softmax", 2)])
 def test_response_band_matches_oracle(distr, out_nl, filt_nl, subunits):
     """compute_ci: y_pred / y_pred_upper / y_pred_lower of _get_response_variance (_glm.py:1166-1232) for
     train and dev.  The oracle follows the reference literally (band lines from the raw lagged design
@@ -615,6 +617,60 @@ def test_softmax_output_matches_oracle(distr, filt_nl, subunits, dev):
         m.fit(y=fit_y, num_iters=40, alpha=1.0, beta=0.01 if distr == "poisson" else 0.0, metric="corrcoef",
               step_size=0.02 if distr == "poisson" else 0.005, tolerance=0, verbose=0)
     _compare_fit(g, o, dev)
+
+
+@pytest.mark.parametrize("distr,out_nl,subunits,dev", [("poisson", "softplus", 1, True), ("gaussian", "none", 1, False),
+                                                      ("poisson", "softmax", 2, True), ("gaussian", "none", 6, True),
+                                                      ("poisson", "exponential", 3, False)])
+def test_softmax_filter_matches_oracle(distr, out_nl, subunits, dev):
+    """filter_nonlinearity='softmax' (GLM.fnl reached from forwardpass, _glm.py:134-140,561-565): every such
+    filter's output is exp(a_t) / sum over ALL samples of the data set.  The engine runs a preparatory sweep
+    for the normalisers Z_h and the vectors sum exp(a) x, the ordinary sweep with exp(a) / Z_h, and corrects
+    the summed gradient with the cross-sample term of the softmax Jacobian (csrc/softmax.cuh).  One and two
+    softmax heads run on the register-resident sweeps, six (+ history) on the generic one."""
+    n = 2400
+    stim, y, _ = helpers.lnp_data(n, (8, 5, 4), seed=41)
+    y = (y / max(1.0, y.sum())).astype(np.float32) if distr == "gaussian" else y
+    n_tr = 1800 if dev else n
+    g, o = _pair(distr, out_nl)
+    for m in (g, o):
+        m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity="softmax",
+                            name="stimulus")
+        m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
+        if dev:
+            m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
+            m.add_design_matrix(y[n_tr:], name="history", kind="dev")
+        m.initialize(num_subunits=subunits, method="random", random_seed=3, compute_ci=False)
+    _same_p0([o, g], scale=0.1, icpt=0.02)
+    if subunits > 1:
+        for k, name in enumerate(o.filter_names):
+            bump = (0.05 * np.random.default_rng(40 + k).standard_normal(np.asarray(o.p0[name]).shape)).astype(np.float32)
+            o.p0[name] = o.p0[name] + bump
+            g.p0[name] = (g.p0[name] + bump).astype(np.float32)
+    fit_y = {"train": y[:n_tr]}
+    if dev:
+        fit_y["dev"] = y[n_tr:]
+    for m in (g, o):
+        m.y["train"] = np.asarray(y[:n_tr])[m.burn_in:].astype(m.dtype)
+        m.alpha, m.beta = 1.0, 0.01
+    g._dirty = True
+    vg, gg = g.value_and_grad(g.p0, "train")
+    vo, go = o.value_and_grad(o.p0, "train")
+    assert abs(vg - vo) < 1e-5 * abs(vo)
+    for name in o.filter_names:
+        scale = max(np.abs(go[name]).max(), 1e-300)
+        assert np.abs(gg[name] - go[name]).max() < 5e-4 * scale, name
+        # a shift of a softmax filter's drive does not change its output: exactly zero here
+        if g.filter_nonlinearity[name] == "softmax":
+            assert gg["intercept"][name] == 0.0 and abs(float(go["intercept"][name])) < 1e-9 * max(1.0, abs(vo))
+    r_g, r_o = np.asarray(g.forwardpass(g.p0, "train"), np.float64), np.asarray(o.forwardpass(o.p0, "train"), np.float64)
+    assert _wrel(r_g, r_o) < 1e-5
+    for m in (g, o):
+        m.fit(y=fit_y, num_iters=40, alpha=1.0, beta=0.01 if distr == "poisson" else 0.0, metric="corrcoef",
+              step_size=0.02 if distr == "poisson" else 0.005, tolerance=0, verbose=0)
+    # (Gaussian cases: predictions are ~K/n with a relative spread of a few per cent, so a correlation
+    # coefficient formed from fp32 products carries ~1e-5 of cancellation error)
+    _compare_fit(g, o, dev, metric_tol=1e-5 if distr == "poisson" else 1e-4)
 
 
 def test_generic_sweep_wide_design_without_basis():

@@ -188,7 +188,7 @@ def test_design_errors():
         _glm().add_design_matrix(np.zeros((50, 4), np.float32), dims=[5, 3], df=[3, 3], smooth="cr")
     with pytest.raises(NotImplementedError):
         _glm().add_design_matrix(np.zeros(50, np.float32), dims=[5], df=[3], smooth="cr",
-                                 filter_nonlinearity="softmax")
+                                 filter_nonlinearity="swish")
     with pytest.raises(NotImplementedError):
         _glm(distr="binomial")
     with pytest.raises(ValueError):
@@ -309,12 +309,9 @@ def test_block_matmul_runs_on_the_device():
 
 
 def test_refusals_are_pinned():
-    """`softmax` as a FILTER nonlinearity (a normalisation over all samples per filter, _glm.py:134-140
-    reached from :561-565) is refused -- documented in INTEGRATION.md; float64 is accepted with a warning."""
+    """Unknown nonlinearities raise as the reference does (_glm.py:167-170); float64 is accepted with a warning."""
     stim = np.zeros((50, 3), np.float32)
-    m = _glm(distr="poisson", output_nonlinearity="softmax")          # as the OUTPUT nonlinearity it exists
-    with pytest.raises(NotImplementedError):
-        m.add_design_matrix(stim, dims=[4, 3], df=[3, 3], smooth="cr", filter_nonlinearity="softmax")
+    m = _glm(distr="poisson", output_nonlinearity="softmax")
     with pytest.raises(NotImplementedError):
         m.add_design_matrix(stim, dims=[4, 3], df=[3, 3], smooth="cr", filter_nonlinearity="swish")
     with pytest.warns(UserWarning, match="float32"):
