@@ -94,6 +94,15 @@ CASES = {
     "ci_gaussian_mle": _case(data="g3d", distr="gaussian", out_nl="none", filt_nl="none", subunits=1,
                              split=(0.6, 0.2), hist=(5, 3), init="mle", alpha=1, beta=0.001, step=0.03,
                              metric="mse", history=True, dev=True, iters=50, compute_ci=True, test=True),
+    # 'softmax' (GLM.fnl, _glm.py:134-140: a normalisation over all samples) as filter and as output nonlinearity
+    "softmax_filter_2sub_dev": _case(distr="poisson", out_nl="softplus", filt_nl="softmax", subunits=2,
+                                     alpha=1.0, beta=0.01, step=0.02, metric="corrcoef", history=True, dev=True,
+                                     iters=40),
+    "softmax_output": _case(distr="poisson", out_nl="softmax", filt_nl="none", subunits=1,
+                            alpha=1.0, beta=0.01, step=0.02, metric="corrcoef", history=True, dev=True, iters=40),
+    "softmax_both_gaussian": _case(distr="gaussian", out_nl="softmax", filt_nl="softmax", subunits=1,
+                                   alpha=1.0, beta=0.0, step=0.005, metric="mse", history=True, dev=False,
+                                   iters=40),
 }
 
 

@@ -67,6 +67,14 @@ def _compare(got, want, rtol, skip=()):
         assert _rel(g, w) <= rtol, (key, _rel(g, w))
 
 
+def _softmax_skip(name):
+    """A softmax does not depend on a shift of its argument: the gradient of the intercepts below it is rounding
+    noise (1e-17 of the cost in float64), which Adam's normalisation turns into ~1e-9 of drift.  Those intercepts
+    have no effect on any prediction and are not compared; everything they could influence is."""
+    c = gc.CASES[name]
+    return ("last.intercept", "opt.intercept") if "softmax" in (c["out_nl"], c["filt_nl"]) else ()
+
+
 def _golden_case(z, name, tag):
     prefix = f"{name}/{tag}/"
     return {k[len(prefix):]: z[k] for k in z.files if k.startswith(prefix)}
@@ -225,6 +233,7 @@ def test_oracle_equals_live_reference(ref, golden_glm, name):
         # float32: intercepts of 'none' filters are interchangeable directions -- Adam normalises
         # rounding noise there; they are checked through the predictions instead
         skip = () if tag == "f64" else ("last.intercept", "opt.intercept", "V.", "b_se.", "w_se.")
+        skip = skip + _softmax_skip(name)
         _compare(o, r, rtol, skip=skip)
         if backend == "shim":          # the committed fixtures are what the live reference gives
             want = _golden_case(golden_glm, name, tag)
@@ -256,7 +265,7 @@ def test_oracle_reproduces_reference_fixtures(golden_glm, name):
         pytest.fail("this platform regenerates different inputs than the fixtures were made from")
     o = gc.summarize(*gc.run_case(lambda d, o_: OracleGLM(distr=d, output_nonlinearity=o_, dtype=np.float64),
                                   name, np.float64, data=data))
-    _compare(o, _golden_case(golden_glm, name, "f64"), F64_RTOL)
+    _compare(o, _golden_case(golden_glm, name, "f64"), F64_RTOL, skip=_softmax_skip(name))
 
 
 def test_fixture_inventory(golden_glm):
