@@ -183,6 +183,215 @@ __global__ void __launch_bounds__(kGramThreads) gram_kernel(const GramArgs a) {
   }
 }
 
+// ---- the same tile pair on the FP64 tensor-core path (round 2) -------------------------------------------------
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) runs at the DFMA rate on B200 (18.5 vs 17.8 T/s measured,
+// tools/micro/dmma_rate.cu) but needs one 8-byte shared load per 256 multiply-adds where the register-tile kernel
+// above needs eight 16-byte loads per 2048: the FP64 pipe, not operand delivery, becomes the limit.
+// 4 warps per CTA.  Off the diagonal warp (wi, wj) owns the 32 x 32 quadrant of the 64 x 64 tile pair = 4 x 4 DMMA
+// blocks; on it only block columns >= block row are computed (the rest is the mirror image): warp w takes block
+// rows w and 7 - w, 8 - w and w + 1 blocks, nine per warp.  32 accumulator doubles per lane either way.
+// With the stage stored [row k][column] both fragments are the same access,
+//   A[i = lane / 4][k = lane % 4] = P[k0 + lane % 4][i0 + lane / 4],
+// and a row stride of 68 doubles (= 32 B mod 128 B) puts the four k rows a half warp reads (4 columns = 32 B each)
+// into four different bank groups: conflict-free 8-byte loads.
+// Columns past the window are NOT masked: output (r, c) depends on columns r and c only and outputs outside the
+// window are never written, so whatever the padding holds stays in the padding.
+constexpr int kGramMmaThreads = 128;
+constexpr int kGramLd = kGramTile + 4;
+constexpr size_t kGramMmaSmem = 2 * sizeof(double) * kGramKC * kGramLd       // Pa, Pb
+                                + 2 * sizeof(float) * kGramKC * kGramTile    // Fa, Fb
+                                + 3 * sizeof(float) * kGramKC;               // row weights, responses (x2)
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+// one 32-row stage of an off-diagonal tile pair: NI x NJ blocks of this warp's quadrant
+template <int NI, int NJ>
+__device__ __forceinline__ void gram_stage_offdiag(double (&acc)[4][4][2], const double (*Pa)[kGramLd],
+                                                   const double (*Pb)[kGramLd], int fk, int ca, int cb) {
+#pragma unroll
+  for (int k0 = 0; k0 < kGramKC; k0 += 4) {
+    double av[NI], bv[NJ];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) av[i] = Pa[k0 + fk][ca + i * 8];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) bv[j] = Pb[k0 + fk][cb + j * 8];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dmma_8x8x4(acc[i][j], av[i], bv[j]);
+  }
+}
+// one stage of a diagonal tile for warp W: block rows W and 7 - W against block columns j >= row, j < ND.
+// acc[2 r + (j >> 2)][j & 3] with r = 0 for row W, 1 for row 7 - W.
+template <int W, int ND>
+__device__ __forceinline__ void gram_stage_diag(double (&acc)[4][4][2], const double (*Pa)[kGramLd],
+                                                const double (*Pb)[kGramLd], int fk, int fc) {
+#pragma unroll
+  for (int k0 = 0; k0 < kGramKC; k0 += 4) {
+    double av[2], bv[8];
+    av[0] = Pa[k0 + fk][W * 8 + fc];             // (Pa carries the row weight, Pb does not)
+    av[1] = Pa[k0 + fk][(7 - W) * 8 + fc];
+#pragma unroll
+    for (int j = W; j < ND; ++j) bv[j] = Pb[k0 + fk][j * 8 + fc];
+#pragma unroll
+    for (int j = W; j < ND; ++j) {
+      if (W < ND) dmma_8x8x4(acc[j >> 2][j & 3], av[0], bv[j]);
+      if (j >= 7 - W) dmma_8x8x4(acc[2 + (j >> 2)][j & 3], av[1], bv[j]);
+    }
+  }
+}
+template <int ND>
+__device__ __forceinline__ void gram_stage_diag_w(int warp, double (&acc)[4][4][2], const double (*Pa)[kGramLd],
+                                                  const double (*Pb)[kGramLd], int fk, int fc) {
+  switch (warp) {
+    case 0: gram_stage_diag<0, ND>(acc, Pa, Pb, fk, fc); break;
+    case 1: gram_stage_diag<1, ND>(acc, Pa, Pb, fk, fc); break;
+    case 2: gram_stage_diag<2, ND>(acc, Pa, Pb, fk, fc); break;
+    default: gram_stage_diag<3, ND>(acc, Pa, Pb, fk, fc); break;
+  }
+}
+
+__global__ void __launch_bounds__(kGramMmaThreads, 4) gram_mma_kernel(const GramArgs a) {
+  extern __shared__ __align__(16) unsigned char gram_smem[];
+  double (*Pa)[kGramLd] = reinterpret_cast<double (*)[kGramLd]>(gram_smem);
+  double (*Pb)[kGramLd] = Pa + kGramKC;
+  float (*Fa)[kGramTile] = reinterpret_cast<float (*)[kGramTile]>(gram_smem + 2 * sizeof(double) * kGramKC * kGramLd);
+  float (*Fb)[kGramTile] = Fa + kGramKC;
+  float* Fw = reinterpret_cast<float*>(Fb + kGramKC);
+  float* Fy = Fw + kGramKC;
+  float* Py = Fy + kGramKC;
+  int pair = blockIdx.x, ti = 0;
+  while (pair >= a.n_tiles - ti) { pair -= a.n_tiles - ti; ++ti; }
+  const int tj = ti + pair;
+  const int slab = blockIdx.y;
+  const long long rows_per_slab = (a.n_rows + a.n_slabs - 1) / a.n_slabs;
+  const long long r_begin = (long long)slab * rows_per_slab;
+  const long long r_end = r_begin + rows_per_slab < a.n_rows ? r_begin + rows_per_slab : a.n_rows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wi = warp >> 1, wj = warp & 1;
+  const int fk = lane & 3, fc = lane >> 2;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double cs = 0.0, cy = 0.0;
+  const bool diag = ti == tj;
+  // 8 x 8 blocks that hold real columns (the window's last tile is usually partial): the rest is skipped
+  const int ni = min(4, max(0, (a.ncols - ti * kGramTile - wi * 32 + 7) / 8));
+  const int nj = min(4, max(0, (a.ncols - tj * kGramTile - wj * 32 + 7) / 8));
+  const int nd = min(8, (a.ncols - ti * kGramTile + 7) / 8);
+
+  // a thread always copies the same four-column piece of rows k_t, k_t + 8, k_t + 16, k_t + 24 of a stage
+  const int k_t = threadIdx.x >> 4, sc_t = (threadIdx.x & 15) * 4;
+  const float* src_a = gram_src4(a, 0, ti * kGramTile + sc_t);
+  const float* src_b = diag ? nullptr : gram_src4(a, 0, tj * kGramTile + sc_t);
+  long long ld_a = 0, ld_b = 0;
+  {
+    auto ld_of = [&](int col) {
+      const int gc = col + a.col_lo;
+      int s = 0;
+      while (s + 1 < a.n_slots && gc >= a.slot_col0[s + 1]) ++s;
+      return a.slot_ld[s];
+    };
+    if (src_a) ld_a = ld_of(ti * kGramTile + sc_t);
+    if (src_b) ld_b = ld_of(tj * kGramTile + sc_t);
+  }
+  auto issue = [&](long long r0) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int k = k_t + 8 * h;
+      const long long row = r0 + k;
+      const bool ok = row < r_end;
+      gram_cp16(&Fa[k][sc_t], (ok && src_a) ? src_a + row * ld_a : nullptr);
+      if (!diag) gram_cp16(&Fb[k][sc_t], (ok && src_b) ? src_b + row * ld_b : nullptr);
+    }
+    if (threadIdx.x < kGramKC) {
+      const long long row = r0 + threadIdx.x;
+      gram_cp4(&Fw[threadIdx.x], (a.wgt != nullptr && row < r_end) ? a.wgt + row : nullptr);
+      gram_cp4(&Fy[threadIdx.x], (a.y != nullptr && row < r_end) ? a.y + row : nullptr);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (r_begin < r_end) issue(r_begin);
+  for (long long r0 = r_begin; r0 < r_end; r0 += kGramKC) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                 // stage landed for everyone; everyone finished the previous products
+    // fp32 -> fp64, two columns per thread and step: a quarter warp stores 128 contiguous bytes
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int idx = threadIdx.x + kGramMmaThreads * h;
+      const int k = idx >> 5, sc = (idx & 31) * 2;
+      const float2 xa = *reinterpret_cast<const float2*>(&Fa[k][sc]);
+      const float2 xb = diag ? xa : *reinterpret_cast<const float2*>(&Fb[k][sc]);
+      // the weight rides on the left factor (product formed in fp32, as XS.T * U does in the reference)
+      if (a.wgt != nullptr) {
+        const float wv = Fw[k];
+        *reinterpret_cast<double2*>(&Pa[k][sc]) = make_double2((double)(xa.x * wv), (double)(xa.y * wv));
+      } else {
+        *reinterpret_cast<double2*>(&Pa[k][sc]) = make_double2((double)xa.x, (double)xa.y);
+      }
+      *reinterpret_cast<double2*>(&Pb[k][sc]) = make_double2((double)xb.x, (double)xb.y);
+    }
+    if (threadIdx.x < kGramKC) Py[threadIdx.x] = Fy[threadIdx.x];
+    __syncthreads();                 // float64 stage complete, fp32 stage free again
+    if (r0 + kGramKC < r_end) issue(r0 + kGramKC);
+    if (!diag) {
+      const int ca = wi * 32 + fc, cb = wj * 32 + fc;
+      if (ni == 4 && nj == 4) gram_stage_offdiag<4, 4>(acc, Pa, Pb, fk, ca, cb);
+      else if (ni == 4 && nj == 1) gram_stage_offdiag<4, 1>(acc, Pa, Pb, fk, ca, cb);
+      else if (ni == 4 && nj == 2) gram_stage_offdiag<4, 2>(acc, Pa, Pb, fk, ca, cb);
+      else if (ni == 4 && nj == 3) gram_stage_offdiag<4, 3>(acc, Pa, Pb, fk, ca, cb);
+      // (ni < 4 only happens in the last tile, which is never the left one of an off-diagonal pair; nj == 0: nothing)
+    } else {
+      if (nd == 8) gram_stage_diag_w<8>(warp, acc, Pa, Pb, fk, fc);
+      else if (nd > 4) gram_stage_diag_w<8>(warp, acc, Pa, Pb, fk, fc);   // partial: whole tile, padding unused
+      else gram_stage_diag_w<4>(warp, acc, Pa, Pb, fk, fc);
+      if (threadIdx.x < kGramTile) {
+#pragma unroll 8
+        for (int k = 0; k < kGramKC; ++k) {
+          const double v = Pa[k][threadIdx.x];
+          cs += v;
+          cy = fma(v, (double)Py[k], cy);
+        }
+      }
+    }
+  }
+  double* out = a.part + (size_t)slab * ((size_t)a.ncols * a.ncols + 2 * (size_t)a.ncols);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int r, c;
+        bool mirror = true;
+        if (!diag) {
+          r = ti * kGramTile + wi * 32 + i * 8 + fc;
+          c = tj * kGramTile + wj * 32 + j * 8 + 2 * fk + e;
+        } else {
+          const int br = i < 2 ? warp : 7 - warp, bj = 4 * (i & 1) + j;
+          if (bj < br) continue;                       // below the diagonal: never computed
+          mirror = bj > br;                            // a diagonal block holds both of its triangles itself
+          r = ti * kGramTile + br * 8 + fc;
+          c = ti * kGramTile + bj * 8 + 2 * fk + e;
+        }
+        if (r < a.ncols && c < a.ncols) {
+          out[(size_t)r * a.ncols + c] = acc[i][j][e];
+          if (mirror) out[(size_t)c * a.ncols + r] = acc[i][j][e];
+        }
+      }
+  if (diag && threadIdx.x < kGramTile) {
+    const int c = ti * kGramTile + threadIdx.x;
+    if (c < a.ncols) {
+      out[(size_t)a.ncols * a.ncols + c] = cs;
+      out[(size_t)a.ncols * a.ncols + a.ncols + c] = cy;
+    }
+  }
+}
+
 // w <- 1 / r^2 in place (the weights of the Poisson filter covariance, _glm.py:1129-1131)
 __global__ void __launch_bounds__(256) inv_square_kernel(float* r, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

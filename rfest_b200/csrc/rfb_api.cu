@@ -129,6 +129,7 @@ struct rfb_engine {
   double last_project_h2d_bytes = 0.0;
   int sweep_pool_ctas = 0;     // CTAs of the pooled subunit sweep (0: one per SM); tests shrink it to force stage reuse
   int fit_small_ctas = 0;      // CTAs of the persistent small-model kernel (0: sized from the row count)
+  int gram_mma = 1;            // Gram matrices on the FP64 tensor-core path (gram_mma_kernel); 0: register-tile DFMA kernel
   int fit_persistent = 1;      // small models: one persistent cooperative kernel for the whole loop (fit_small.cuh)
   int project_slab_rows = 0;   // rows per projection slab (0: sized from the frame size); tests shrink it
   int project_tc = 1;     // spatial projection on tensor cores (tcgen05, 3xTF32) when the shape allows
@@ -1003,6 +1004,7 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   if (const char* v = getenv("RFB_H2D_THREADS")) e->h2d_threads = std::max(1, atoi(v));
   if (const char* v = getenv("RFB_H2D_OVERLAP")) e->h2d_overlap = atoi(v);
   if (const char* v = getenv("RFB_FIT_PERSISTENT")) e->fit_persistent = atoi(v);
+  if (const char* v = getenv("RFB_GRAM_MMA")) e->gram_mma = atoi(v);
   if (const char* v = getenv("RFB_FIT_SMALL_CTAS")) e->fit_small_ctas = std::max(0, atoi(v));
   *out = e;
   return RFB_OK;
@@ -1021,6 +1023,7 @@ extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) 
   else if (k == "h2d_threads") e->h2d_threads = std::max(1, value);
   else if (k == "h2d_overlap") e->h2d_overlap = value;
   else if (k == "fit_persistent") e->fit_persistent = value;
+  else if (k == "gram_mma") e->gram_mma = value;
   else if (k == "sweep_pool_ctas") e->sweep_pool_ctas = std::max(0, value);
   else if (k == "fit_small_ctas") e->fit_small_ctas = std::max(0, value);
   else if (k == "project_slab_rows") e->project_slab_rows = std::max(0, value);
@@ -2015,14 +2018,18 @@ static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float*
   a.n_tiles = (ncols + kGramTile - 1) / kGramTile;
   a.n_pairs = a.n_tiles * (a.n_tiles + 1) / 2;
   // row slabs: about four balanced waves of CTAs (4 resident per SM: 206 registers x 64 threads), never shorter than 4096 rows
+  // (tile pairs differ in work -- diagonal ones do 36 of 64 blocks -- so the tensor-core kernel takes twelve short
+  // waves rather than four long ones: the ragged end of the launch shrinks with the CTA duration)
   const int resident = 4 * e->num_sms;
-  int slabs = std::max(1, (4 * resident) / a.n_pairs);
+  int slabs = std::max(1, ((e->gram_mma ? 12 : 4) * resident) / a.n_pairs);
   slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, ds.n / 4096));
-  a.n_slabs = slabs;
   const size_t n_entries = (size_t)ncols * ncols + 2 * (size_t)ncols;
+  slabs = (int)std::min<size_t>(slabs, std::max<size_t>(1, ((size_t)256 << 20) / (sizeof(double) * n_entries)));   // <= 256 MB of partial sums
+  a.n_slabs = slabs;
   static bool gram_attr = false;
   if (!gram_attr) {
     CU(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmem));
+    CU(cudaFuncSetAttribute(gram_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramMmaSmem));
     gram_attr = true;
   }
   double *d_part = nullptr, *d_out = nullptr;
@@ -2034,7 +2041,8 @@ static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float*
                 sizeof(double) * n_entries * (slabs + 1));
   }
   a.part = d_part;
-  gram_kernel<<<dim3(a.n_pairs, slabs), kGramThreads, kGramSmem, e->stream>>>(a);
+  if (e->gram_mma) gram_mma_kernel<<<dim3(a.n_pairs, slabs), kGramMmaThreads, kGramMmaSmem, e->stream>>>(a);
+  else gram_kernel<<<dim3(a.n_pairs, slabs), kGramThreads, kGramSmem, e->stream>>>(a);
   gram_reduce_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, e->stream>>>(d_part, slabs, (long long)n_entries, d_out);
   e->launches += 2;
   cudaError_t ce = cudaGetLastError();
