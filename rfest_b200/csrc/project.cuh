@@ -149,21 +149,14 @@ __constant__ float c_st[kTempMaxLag * 16];
 // pair and are updated by one fma.rn.f32x2 (SASS FFMA2) -- two IEEE fused multiply-adds, bit-identical to the
 // scalar ones, for one issue slot.  The kernel was issue-bound (65 % of its instructions were FFMAs at 75 %
 // issue utilisation); halving the FMA instructions puts it on the FMA pipe itself.
-template <int DFT, bool FAST>
-__device__ __forceinline__ void temporal_accumulate(const TemporalArgs& a, long long src0, int q, float (&acc)[8][DFT]) {
+// `zload(k)` returns the value of the thread's column in the k-th raw row of its window (k = 0 .. nlag + 6).
+// (The basis is read from constant memory through uniform registers; a shared-memory copy feeding ordinary
+// registers was tried and measured no faster.)
+template <int DFT, class Load>
+__device__ __forceinline__ void temporal_accumulate_from(int nlag, Load zload, float (&acc)[8][DFT]) {
   constexpr int TT = 8;
   constexpr bool PACKED = (DFT % 2) == 0;
   constexpr int DP = PACKED ? DFT / 2 : 1;
-  const float* zp = nullptr;
-  const long long ldz = a.ldz;
-  if (FAST) zp = a.Z + (src0 - a.z_src0) * ldz + q;
-  auto zload = [&](int k) -> float {                // raw row src0 + k of column q
-    if (FAST) return __ldg(zp + k * ldz);
-    const long long src = src0 + k;
-    if (src < 0 || src >= a.n_raw_total) return 0.f;
-    const long long zr = src - a.z_src0;
-    return (zr >= 0 && zr < a.n_z) ? __ldg(a.Z + zr * ldz + q) : 0.f;
-  };
   u64_t acc2[TT][DP];
   if (PACKED) {
 #pragma unroll
@@ -196,14 +189,14 @@ __device__ __forceinline__ void temporal_accumulate(const TemporalArgs& a, long 
 
   float w[2 * TT - 1];                              // Z[src0 + i0 + k], k = 0 .. 14
   float nx[TT];                                     // the 8 values the NEXT step adds, loaded one step ahead
-  const int last = a.nlag + TT - 2;                 // last raw row (relative) any lag of this thread reads
+  const int last = nlag + TT - 2;                   // last raw row (relative) any lag of this thread reads
 #pragma unroll
   for (int k = 0; k < TT - 1; ++k) w[k] = zload(k);
 #pragma unroll
   for (int k = 0; k < TT; ++k) nx[k] = zload(min(TT - 1 + k, last));
   int i0 = 0;
 #pragma unroll 1
-  for (; i0 + TT <= a.nlag; i0 += TT) {
+  for (; i0 + TT <= nlag; i0 += TT) {
 #pragma unroll
     for (int k = 0; k < TT; ++k) w[TT - 1 + k] = nx[k];
 #pragma unroll
@@ -214,7 +207,7 @@ __device__ __forceinline__ void temporal_accumulate(const TemporalArgs& a, long 
 #pragma unroll
     for (int k = 0; k < TT - 1; ++k) w[k] = w[k + TT];
   }
-  const int rem = a.nlag - i0;                      // 0 .. 7 lags left
+  const int rem = nlag - i0;                        // 0 .. 7 lags left
   if (rem > 0) {
 #pragma unroll
     for (int k = 0; k < TT - 1; ++k) w[TT - 1 + k] = nx[k];
@@ -229,6 +222,21 @@ __device__ __forceinline__ void temporal_accumulate(const TemporalArgs& a, long 
 #pragma unroll
       for (int dp = 0; dp < DP; ++dp) unpack2(acc2[tt][dp], acc[tt][2 * dp], acc[tt][2 * dp + 1]);
   }
+}
+
+template <int DFT, bool FAST>
+__device__ __forceinline__ void temporal_accumulate(const TemporalArgs& a, long long src0, int q, float (&acc)[8][DFT]) {
+  const float* zp = nullptr;
+  const long long ldz = a.ldz;
+  if (FAST) zp = a.Z + (src0 - a.z_src0) * ldz + q;
+  auto zload = [&](int k) -> float {                // raw row src0 + k of column q
+    if (FAST) return __ldg(zp + k * ldz);
+    const long long src = src0 + k;
+    if (src < 0 || src >= a.n_raw_total) return 0.f;
+    const long long zr = src - a.z_src0;
+    return (zr >= 0 && zr < a.n_z) ? __ldg(a.Z + zr * ldz + q) : 0.f;
+  };
+  temporal_accumulate_from<DFT>(a.nlag, zload, acc);
 }
 
 template <int DFT>

@@ -129,6 +129,7 @@ struct rfb_engine {
   double last_project_h2d_bytes = 0.0;
   int sweep_pool_ctas = 0;     // CTAs of the pooled subunit sweep (0: one per SM); tests shrink it to force stage reuse
   int fit_small_ctas = 0;      // CTAs of the persistent small-model kernel (0: sized from the row count)
+  int project_fused = 0;       // 1: spatial + temporal projection of a slab in ONE kernel where the shape allows (measured slower: DESIGN 3.1)
   int gram_mma = 1;            // Gram matrices on the FP64 tensor-core path (gram_mma_kernel); 0: register-tile DFMA kernel
   int fit_persistent = 1;      // small models: one persistent cooperative kernel for the whole loop (fit_small.cuh)
   int project_slab_rows = 0;   // rows per projection slab (0: sized from the frame size); tests shrink it
@@ -1005,6 +1006,7 @@ extern "C" int rfb_engine_create(int device, rfb_engine** out) {
   if (const char* v = getenv("RFB_H2D_OVERLAP")) e->h2d_overlap = atoi(v);
   if (const char* v = getenv("RFB_FIT_PERSISTENT")) e->fit_persistent = atoi(v);
   if (const char* v = getenv("RFB_GRAM_MMA")) e->gram_mma = atoi(v);
+  if (const char* v = getenv("RFB_PROJECT_FUSED")) e->project_fused = atoi(v);
   if (const char* v = getenv("RFB_FIT_SMALL_CTAS")) e->fit_small_ctas = std::max(0, atoi(v));
   *out = e;
   return RFB_OK;
@@ -1024,6 +1026,7 @@ extern "C" int rfb_engine_set_option(rfb_engine* e, const char* key, int value) 
   else if (k == "h2d_overlap") e->h2d_overlap = value;
   else if (k == "fit_persistent") e->fit_persistent = value;
   else if (k == "gram_mma") e->gram_mma = value;
+  else if (k == "project_fused") e->project_fused = value;
   else if (k == "sweep_pool_ctas") e->sweep_pool_ctas = std::max(0, value);
   else if (k == "fit_small_ctas") e->fit_small_ctas = std::max(0, value);
   else if (k == "project_slab_rows") e->project_slab_rows = std::max(0, value);
@@ -1302,6 +1305,10 @@ struct TcPlan {
   bool ok = false;
   int n_pad = 0, k_tiles = 0, stages = 0, tmem_cols = 0, drain = 4, n_raw = 0;
   size_t smem = 0;
+  // fused spatial + temporal variant (Z ring in shared memory): fewer raw A slots fit
+  bool fused_ok = false;
+  int fused_n_raw = 0;
+  size_t fused_smem = 0;
   const float *bhi = nullptr, *blo = nullptr;   // device, [n_pad x k_tiles*32], K contiguous
   CUtensorMap map_bhi, map_blo;
 };
@@ -1353,12 +1360,26 @@ static int tc_prepare(rfb_engine* e, const float* Sxy, int n_pix, int n_q, TcPla
   tp->blo = tp->bhi + (size_t)tp->n_pad * kpad;
   if (!make_map_2d(&tp->map_bhi, tp->bhi, tp->n_pad, kpad, kpad, tp->n_pad)) return RFB_OK;
   if (!make_map_2d(&tp->map_blo, tp->blo, tp->n_pad, kpad, kpad, tp->n_pad)) return RFB_OK;
-  if (cudaFuncSetAttribute(spatial_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp->smem) !=
-      cudaSuccess) {
+  if (cudaFuncSetAttribute(spatial_project_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)tp->smem) != cudaSuccess) {
     cudaGetLastError();
     return RFB_OK;
   }
   tp->ok = true;
+  if (e->project_fused && n_q <= kTcFusedMaxN) {
+    const size_t ring = tc_ring_bytes(n_q);
+    if (fixed + ring + 3 * kTcRawBytes <= budget) {
+      tp->fused_n_raw = (int)std::min<size_t>(8, (budget - fixed - ring) / kTcRawBytes);
+      if (const char* v = getenv("RFB_TC_NRAW")) tp->fused_n_raw = std::max(2, std::min(tp->fused_n_raw, atoi(v)));
+      tp->fused_smem = tc_smem_bytes(tp->n_pad, tp->stages, tp->fused_n_raw, ring);
+      tp->fused_ok =
+          cudaFuncSetAttribute(spatial_project_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tp->fused_smem) == cudaSuccess &&
+          cudaFuncSetAttribute(spatial_project_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tp->fused_smem) == cudaSuccess;
+      if (!tp->fused_ok) cudaGetLastError();
+    }
+  }
   return RFB_OK;
 }
 
@@ -1381,7 +1402,47 @@ static bool tc_launch(rfb_engine* e, const TcPlan& tp, const float* d_stim, int6
   a.n_raw = tp.n_raw;
   const int64_t tiles = (nz + kTcM - 1) / kTcM;
   const int grid = (int)std::min<int64_t>(tiles, e->num_sms);
-  spatial_project_tc_kernel<<<grid, kTcThreads, tp.smem, e->stream>>>(map_a, tp.map_bhi, tp.map_blo, a);
+  spatial_project_tc_kernel<false, 8><<<grid, kTcThreads, tp.smem, e->stream>>>(map_a, tp.map_bhi, tp.map_blo, a,
+                                                                                TcFuseArgs{});
+  e->launches++;
+  return true;
+}
+
+// Spatial + temporal contraction of one slab in ONE kernel (project_tc.cuh, FUSED): returns false if the slab
+// cannot take this path.  `off`: Z row feeding (design row 0 of the slab, lag 0), <= 0.
+static bool tc_launch_fused(rfb_engine* e, const TcPlan& tp, const float* d_stim, int64_t nz, int n_pix, int n_q,
+                            int DFT, const TemporalArgs& t, int64_t off) {
+  if (!tp.fused_ok || ((uintptr_t)d_stim & 15u) != 0 || (DFT != 4 && DFT != 8)) return false;
+  if (off > 0 || off < -(int64_t)(t.nlag - 1) || t.nlag > kTempMaxLag || nz < 1) return false;
+  CUtensorMap map_a;
+  if (!make_map_2d(&map_a, d_stim, (uint64_t)nz, (uint64_t)n_pix, (uint64_t)n_pix, kTcM)) return false;
+  TcArgs a{};
+  a.n_rows = nz;
+  a.n_k_tiles = tp.k_tiles;
+  a.n = n_q;
+  a.n_pad = tp.n_pad;
+  a.n_stages = tp.stages;
+  a.Z = nullptr;
+  a.ldz = n_q;
+  a.tmem_cols = tp.tmem_cols;
+  a.drain = tp.drain;
+  a.n_raw = tp.fused_n_raw;
+  TcFuseArgs f{};
+  f.off = off;
+  f.n_out = t.n_out;
+  f.out = t.out;
+  f.out_ld = t.out_ld;
+  f.out_row0 = t.out_row0;
+  f.col0 = t.col0;
+  f.nlag = t.nlag;
+  f.df_t = t.df_t;
+  f.n_tiles = (off + t.n_out + t.nlag - 1 + kTcM - 1) / kTcM;
+  if (f.n_tiles < 1) return false;
+  const int grid = (int)std::min<int64_t>(f.n_tiles, e->num_sms);
+  if (DFT == 8)
+    spatial_project_tc_kernel<true, 8><<<grid, kTcFusedThreads, tp.fused_smem, e->stream>>>(map_a, tp.map_bhi, tp.map_blo, a, f);
+  else
+    spatial_project_tc_kernel<true, 4><<<grid, kTcFusedThreads, tp.fused_smem, e->stream>>>(map_a, tp.map_bhi, tp.map_blo, a, f);
   e->launches++;
   return true;
 }
@@ -1584,6 +1645,23 @@ extern "C" int rfb_block_project(rfb_block* dst, int64_t dst_row0, int64_t n_out
         CU(cudaMemcpyAsync(e->stage.p, h_src, bytes, cudaMemcpyHostToDevice, e->stream));
         d_stim = (const float*)e->stage.p;
         e->last_project_h2d_bytes += (double)bytes;
+      }
+      if (Sxy && tcp.fused_ok && groups.size() == 1 && temporal_const) {
+        // one kernel for the slab: Z stays in shared memory
+        TemporalArgs t{};
+        t.out = dst->d;
+        t.out_ld = dst->ld;
+        t.out_row0 = dst_row0 + k0;
+        t.n_out = kc;
+        t.col0 = col0;
+        t.nlag = nlag;
+        t.df_t = groups[0].dw;
+        if (tc_launch_fused(e, tcp, d_stim, nz, n_pix, n_q, groups[0].DFT, t, first_t + k0 - front - lo)) {
+          CU(cudaGetLastError());
+          if (ring) CU(cudaEventRecord(e->ring_consumed[slot], e->stream));
+          if (!on_device && !ring) CU(cudaStreamSynchronize(e->stream));
+          continue;
+        }
       }
       if (Sxy) {
         TRY(scratch_reserve(e, e->zbuf, sizeof(float) * (size_t)nz * n_q));

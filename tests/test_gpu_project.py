@@ -287,6 +287,48 @@ def test_host_ring_equals_device_input_bit_for_bit(slab_rows):
     assert np.abs(outs[0][:276] - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("n,dims,df,shift,slab_rows", [
+    (23000, [25, 20, 15], [8, 6, 6], 0, 0),          # BASELINE config 2-4 shape, one slab
+    (23000, [25, 20, 15], [8, 6, 6], 0, 4100),       # several slabs: ranges, warm-up tiles and slab seams
+    (9000, [25, 20, 15], [8, 6, 6], -3, 2500),       # negative shift: the window reaches into the future
+    (9000, [25, 20, 15], [8, 6, 6], 2, 3000),        # positive shift: the first slab falls back, the rest fuse
+    (700, [12, 8, 8], [4, 4, 4], 0, 0),              # 4 time-basis columns, 16 spatial ones, few tiles
+    (40000, [64, 16, 16], [8, 8, 8], 0, 0),          # the longest lag window, 64 spatial columns
+    (130, [25, 20, 15], [8, 6, 6], 0, 0),            # one and a bit tiles
+])
+def test_fused_projection_equals_the_two_kernel_path_bit_for_bit(n, dims, df, shift, slab_rows):
+    """K1 fused (csrc/project_tc.cuh, FUSED: the temporal Hankel contraction runs inside the tensor-core kernel on
+    a shared-memory ring of Z tiles) must reproduce the two-kernel path exactly -- same Z, same order of the lag
+    sums -- whatever the slab size, tile ranges per CTA or shift; and both follow the oracle."""
+    import torch
+
+    from rfest_b200.engine import Engine
+
+    rng = np.random.default_rng(n + shift)
+    stim = rng.standard_normal((n, dims[1], dims[2])).astype(np.float32)
+    x = torch.from_numpy(stim).cuda()
+    eng = Engine.get()
+    outs = {}
+    try:
+        eng.set_option("project_slab_rows", slab_rows)
+        for fused in (1, 0):
+            eng.set_option("project_fused", fused)
+            m = _glm(distr="gaussian")
+            launches = eng.launch_count
+            m.add_design_matrix(x, dims=dims, df=df, smooth="cr", shift=shift, name="stimulus")
+            outs[fused] = (np.asarray(m.XS["train"]["stimulus"]), eng.launch_count - launches)
+    finally:
+        eng.set_option("project_slab_rows", 0)
+        eng.set_option("project_fused", 0)
+    assert outs[1][1] < outs[0][1]                               # fewer kernels: the fused path really ran
+    assert np.array_equal(outs[1][0], outs[0][0])
+    k = min(n, 400)
+    burn = dims[0] - 1                                           # the default burn-in (_glm.py:250-253)
+    ref = _oracle_xs(stim[:k], dims, df, shift, burn)
+    ok = len(ref) - max(0, -shift)                  # (rows whose window would reach past the truncated copy)
+    assert ok > 0 and np.abs(outs[1][0][:ok] - ref[:ok]).max() <= 2e-6 * np.abs(ref).max()
+
+
 def test_block_matmul_runs_on_the_device():
     rng = np.random.default_rng(2)
     stim = rng.standard_normal((5000, 6, 5)).astype(np.float32)
