@@ -27,6 +27,7 @@ extras   (N=1 only, after the headline; `--no-extras` skips them) `other_configs
 """
 
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -315,6 +316,35 @@ def gpu_arm(args):
         t = torch.tensor([e2e_pred_s], device=f"cuda:{local_rank}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_pred_s = float(t[0])
+    # where that wall clock goes: one more fit with a synchronize after every device-model call (run after the
+    # timed ones; the phases therefore add up to a little more than e2e_s)
+    phases = collections.OrderedDict()
+    dm_e2e = model._dm
+    names = ["set_y", "set_params", "fit_begin", "fit_run", "fit_finish", "fit_traces", "fit_params_all",
+             "fit_predictions_device", "fit_end"]
+    saved = {nm: getattr(dm_e2e, nm) for nm in names if hasattr(dm_e2e, nm)}
+
+    def _wrap(fn, nm):
+        def f(*a, **k):
+            eng.synchronize()
+            t = time.perf_counter()
+            r = fn(*a, **k)
+            eng.synchronize()
+            phases[nm] = phases.get(nm, 0.0) + 1e3 * (time.perf_counter() - t)
+            return r
+        return f
+
+    for nm, fn in saved.items():
+        setattr(dm_e2e, nm, _wrap(fn, nm))
+    barrier()
+    t0 = time.perf_counter()
+    model.fit(y=y_arg, num_iters=K, step_size=STEP_SIZE, beta=BETA, alpha=ALPHA, verbose=0, tolerance=0)
+    eng.synchronize()
+    phases["total_instrumented"] = 1e3 * (time.perf_counter() - t0)
+    phases["host_code_outside"] = phases["total_instrumented"] - sum(v for k, v in phases.items()
+                                                                     if k != "total_instrumented")
+    for nm in saved:
+        delattr(dm_e2e, nm)                 # back to the class's methods
     P = 296
     h2d = (4 * n_local + 4 * P + 8 * 3 + 8 * K) / K
     d2h = (4 * 8 * K + K * (4 * P + 8 * 3)) / K      # traces + every iteration's parameters
@@ -363,6 +393,7 @@ def gpu_arm(args):
                         "predictions stay on the device (as the reference's JAX arrays do) until read. "
                         "K iterations cost K + 1 sweeps (the reference's forward pass at the final parameters "
                         "for metric_train[K-1] / y_pred), so e2e <= K / (K + 1) of `value`",
+                "phases_ms": {k: round(v, 3) for k, v in phases.items()},
                 "with_predictions": {"value": K / e2e_pred_s, "unit": "iterations/s",
                                      "d2h_bytes_per_step": d2h + 4.0 * n_local / K,
                                      "what": "the same call followed by the D2H copy of y_pred['opt']['train'] "

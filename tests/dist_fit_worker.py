@@ -11,10 +11,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def build_and_fit(GLM, stim, y, n_tr, iters, device=None, out_nl=None):
+def build_and_fit(GLM, stim, y, n_tr, iters, device=None, out_nl=None, filt_nl=None):
     out_nl = out_nl or os.environ.get("RFB_TEST_OUT_NL", "softplus")
+    filt_nl = filt_nl or os.environ.get("RFB_TEST_FILT_NL", "none")
     m = GLM(distr="poisson", output_nonlinearity=out_nl, device=device)
-    m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", name="stimulus")
+    m.add_design_matrix(stim[:n_tr], dims=[8, 5, 4], df=[4, 3, 3], smooth="cr", filter_nonlinearity=filt_nl,
+                        name="stimulus")
     m.add_design_matrix(y[:n_tr], dims=[6], df=[4], smooth="cr", shift=1, name="history")
     m.add_design_matrix(stim[n_tr:], name="stimulus", kind="dev")
     m.add_design_matrix(y[n_tr:], name="history", kind="dev")

@@ -19,18 +19,20 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world,xchg,out_nl", [(2, 1, "softplus"), (2, 0, "softplus"), (2, 1, "softmax"),
-                                               (4, 1, "softplus"), (8, 1, "softplus")])
-def test_sharded_fit_matches_single_gpu(world, xchg, out_nl, tmp_path):
+@pytest.mark.parametrize("world,xchg,out_nl,filt_nl", [(2, 1, "softplus", "none"), (2, 0, "softplus", "none"),
+                                                       (2, 1, "softmax", "none"), (2, 1, "softplus", "softmax"),
+                                                       (4, 1, "softplus", "none"), (8, 1, "softplus", "none")])
+def test_sharded_fit_matches_single_gpu(world, xchg, out_nl, filt_nl, tmp_path):
     """xchg=1: gradient exchange by the fused one-shot NVLink kernel; xchg=0: NCCL all-reduce.  With a
-    softmax output the normaliser and the Jacobian scalar are all-reduced inside the iteration as well."""
+    softmax output the normaliser and the Jacobian scalar are all-reduced inside the iteration as well; with a
+    softmax FILTER the per-filter normalisers and the vectors of the Jacobian correction are (NCCL path)."""
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     out = tmp_path / "dist.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "dist_fit_worker.py"), str(out)]
-    env = dict(os.environ, RFB_XCHG=str(xchg), RFB_TEST_OUT_NL=out_nl)
+    env = dict(os.environ, RFB_XCHG=str(xchg), RFB_TEST_OUT_NL=out_nl, RFB_TEST_FILT_NL=filt_nl)
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     got = np.load(out)
@@ -42,7 +44,7 @@ def test_sharded_fit_matches_single_gpu(world, xchg, out_nl, tmp_path):
     from rfest_b200 import GLM
 
     stim, y, _ = helpers.lnp_data(5003, (8, 5, 4), seed=31)
-    one = build_and_fit(GLM, stim, y, 4001, 40, device=0, out_nl=out_nl)
+    one = build_and_fit(GLM, stim, y, 4001, 40, device=0, out_nl=out_nl, filt_nl=filt_nl)
     rel = lambda a, b: np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.abs(np.asarray(b)))  # noqa: E731
     assert rel(got["cost_train"], one.cost_train) < 1e-6
     assert rel(got["cost_dev"], one.cost_dev) < 1e-6
@@ -58,6 +60,6 @@ def test_sharded_fit_matches_single_gpu(world, xchg, out_nl, tmp_path):
         def __init__(self, distr, output_nonlinearity, device=None):
             super().__init__(distr, output_nonlinearity, dtype=np.float64)
 
-    o = build_and_fit(_O, stim, y, 4001, 40, out_nl=out_nl)
+    o = build_and_fit(_O, stim, y, 4001, 40, out_nl=out_nl, filt_nl=filt_nl)
     assert rel(got["cost_train"], o.cost_train) < 1e-5
     assert rel(got["cost_dev"], o.cost_dev) < 1e-5
