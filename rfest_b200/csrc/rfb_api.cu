@@ -2352,12 +2352,12 @@ static int enqueue_iteration(rfb_model* m, bool final_only, float* r_train, floa
       s1 = ReduceSeg{m->sb[RFB_KIND_DEV].cta_part + tail, m->sb[RFB_KIND_DEV].cur_grid, p.NE, kNumScalars, nullptr};
       blocks1 = (kNumScalars + kReduceEx - 1) / kReduceEx;
     }
-    if (e->use_xchg == 2)   // the round-1 multi-CTA form, kept for comparison
-      reduce_exchange_kernel<<<blocks0 + blocks1, dim3(kReduceEx, kReduceEy), 0, e->stream>>>(
-          s0, s1, blocks0, (long long)lo, (long long)p.NE, xchg_args(e, true));
-    else
+    if (e->use_xchg == 3)   // one-CTA form (round 2): measured slower (43 vs 20 us at 2 GPUs), kept for comparison
       reduce_exchange1_kernel<<<1, kReduce1Threads, 0, e->stream>>>(s0, s1, (long long)lo, (long long)p.NE,
                                                                     xchg_args(e, true));
+    else
+      reduce_exchange_kernel<<<blocks0 + blocks1, dim3(kReduceEx, kReduceEy), 0, e->stream>>>(
+          s0, s1, blocks0, (long long)lo, (long long)p.NE, xchg_args(e, true));
     e->launches++;
     CU(cudaGetLastError());
   } else {

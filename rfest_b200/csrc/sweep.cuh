@@ -1049,12 +1049,13 @@ reduce_exchange_kernel(ReduceSeg s0, ReduceSeg s1, int blocks0, long long off0, 
   }
 }
 
-// One-CTA form of the fused reduction + exchange (round 2).  The multi-CTA kernel above needs two system-scope
-// fences in sequence (every CTA before it counts itself done, the last CTA again before it publishes) plus an
-// atomic round trip; measured 23 / 26 / 32 us at 2 / 4 / 8 GPUs for a 2.6 KB vector.  Here one warp owns 32
-// consecutive entries and adds the CTA partial rows in row order (lanes = entries: coalesced, no shared
-// memory, no barrier inside the sum), stores the sums into every peer, and after ONE __syncthreads a single
-// thread issues ONE system-scope fence and the flags.
+// One-CTA form of the fused reduction + exchange (round 2 experiment, `xchg = 3`).  The multi-CTA kernel above needs
+// two system-scope fences in sequence (every CTA before it counts itself done, the last CTA again before it
+// publishes) plus an atomic round trip.  Here one warp owns 32 consecutive entries and adds the CTA partial rows in
+// row order (lanes = entries: coalesced, no shared memory, no barrier inside the sum), stores the sums into every
+// peer, and after ONE __syncthreads a single thread issues ONE system-scope fence and the flags.  Measured SLOWER:
+// 43 us against 20 us at 2 GPUs (rest of the step 52 vs 32 us, `profiles/xchg_variants_r2.txt`) -- 16 warps walking
+// 148-296 partial rows 8 at a time are ~37 dependent L2 round trips; the multi-CTA form spreads them over 11 CTAs.
 constexpr int kReduce1Threads = 512;
 __global__ void __launch_bounds__(kReduce1Threads)
 reduce_exchange1_kernel(ReduceSeg s0, ReduceSeg s1, long long off0, long long off1, XchgArgs x) {

@@ -21,9 +21,10 @@ def _n_gpus():
 
 @pytest.mark.parametrize("world,xchg,out_nl,filt_nl", [(2, 1, "softplus", "none"), (2, 0, "softplus", "none"),
                                                        (2, 1, "softmax", "none"), (2, 1, "softplus", "softmax"),
+                                                       (2, 3, "softplus", "none"),
                                                        (4, 1, "softplus", "none"), (8, 1, "softplus", "none")])
 def test_sharded_fit_matches_single_gpu(world, xchg, out_nl, filt_nl, tmp_path):
-    """xchg=1: gradient exchange by the fused one-shot NVLink kernel; xchg=0: NCCL all-reduce.  With a
+    """xchg=1: gradient exchange by the fused one-shot NVLink kernel (3: its one-CTA variant); xchg=0: NCCL all-reduce.  With a
     softmax output the normaliser and the Jacobian scalar are all-reduced inside the iteration as well; with a
     softmax FILTER the per-filter normalisers and the vectors of the Jacobian correction are (NCCL path)."""
     if _n_gpus() < world:
