@@ -197,20 +197,25 @@ __global__ void __launch_bounds__(kGramThreads) gram_kernel(const GramArgs a) {
 // Columns past the window are NOT masked: output (r, c) depends on columns r and c only and outputs outside the
 // window are never written, so whatever the padding holds stays in the padding.
 constexpr int kGramMmaThreads = 128;
+constexpr int kGramMK = 16;                  // rows per stage of the tensor-core kernel
 constexpr int kGramLd = kGramTile + 4;
-constexpr size_t kGramMmaSmem = 2 * sizeof(double) * kGramKC * kGramLd       // Pa, Pb
-                                + 2 * sizeof(float) * kGramKC * kGramTile    // Fa, Fb
-                                + 3 * sizeof(float) * kGramKC;               // row weights, responses (x2)
+// Shared memory: the float64 stage is double-buffered, so one barrier per stage suffices -- a warp that has
+// finished its products converts the next stage into the other buffer while slower warps still multiply.  Every
+// thread converts exactly the 16-byte pieces it copied itself (cp.async), so the fp32 staging area needs no
+// barrier at all.
+constexpr size_t kGramMmaSmem = 2 * 2 * sizeof(double) * kGramMK * kGramLd   // Pa, Pb x 2 buffers
+                                + 2 * sizeof(float) * kGramMK * kGramTile    // Fa, Fb
+                                + 2 * sizeof(float) * kGramMK;               // responses x 2 buffers
 __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
       : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
-// one 32-row stage of an off-diagonal tile pair: NI x NJ blocks of this warp's quadrant
+// one stage of an off-diagonal tile pair: NI x NJ blocks of this warp's quadrant
 template <int NI, int NJ>
 __device__ __forceinline__ void gram_stage_offdiag(double (&acc)[4][4][2], const double (*Pa)[kGramLd],
                                                    const double (*Pb)[kGramLd], int fk, int ca, int cb) {
 #pragma unroll
-  for (int k0 = 0; k0 < kGramKC; k0 += 4) {
+  for (int k0 = 0; k0 < kGramMK; k0 += 4) {
     double av[NI], bv[NJ];
 #pragma unroll
     for (int i = 0; i < NI; ++i) av[i] = Pa[k0 + fk][ca + i * 8];
@@ -228,7 +233,7 @@ template <int W, int ND>
 __device__ __forceinline__ void gram_stage_diag(double (&acc)[4][4][2], const double (*Pa)[kGramLd],
                                                 const double (*Pb)[kGramLd], int fk, int fc) {
 #pragma unroll
-  for (int k0 = 0; k0 < kGramKC; k0 += 4) {
+  for (int k0 = 0; k0 < kGramMK; k0 += 4) {
     double av[2], bv[8];
     av[0] = Pa[k0 + fk][W * 8 + fc];             // (Pa carries the row weight, Pb does not)
     av[1] = Pa[k0 + fk][(7 - W) * 8 + fc];
@@ -254,13 +259,12 @@ __device__ __forceinline__ void gram_stage_diag_w(int warp, double (&acc)[4][4][
 
 __global__ void __launch_bounds__(kGramMmaThreads, 4) gram_mma_kernel(const GramArgs a) {
   extern __shared__ __align__(16) unsigned char gram_smem[];
-  double (*Pa)[kGramLd] = reinterpret_cast<double (*)[kGramLd]>(gram_smem);
-  double (*Pb)[kGramLd] = Pa + kGramKC;
-  float (*Fa)[kGramTile] = reinterpret_cast<float (*)[kGramTile]>(gram_smem + 2 * sizeof(double) * kGramKC * kGramLd);
-  float (*Fb)[kGramTile] = Fa + kGramKC;
-  float* Fw = reinterpret_cast<float*>(Fb + kGramKC);
-  float* Fy = Fw + kGramKC;
-  float* Py = Fy + kGramKC;
+  typedef double (*PStage)[kGramLd];
+  PStage P0 = reinterpret_cast<PStage>(gram_smem);            // [buffer][Pa | Pb][row][kGramLd]
+  constexpr int kPRows = 2 * kGramMK;                          // rows of one buffer: Pa then Pb
+  float (*Fa)[kGramTile] = reinterpret_cast<float (*)[kGramTile]>(gram_smem + 2 * sizeof(double) * kPRows * kGramLd);
+  float (*Fb)[kGramTile] = Fa + kGramMK;
+  float* Py = reinterpret_cast<float*>(Fb + kGramMK);          // [buffer][row]
   int pair = blockIdx.x, ti = 0;
   while (pair >= a.n_tiles - ti) { pair -= a.n_tiles - ti; ++ti; }
   const int tj = ti + pair;
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(kGramMmaThreads, 4) gram_mma_kernel(const Gram
   const int nj = min(4, max(0, (a.ncols - tj * kGramTile - wj * 32 + 7) / 8));
   const int nd = min(8, (a.ncols - ti * kGramTile + 7) / 8);
 
-  // a thread always copies the same four-column piece of rows k_t, k_t + 8, k_t + 16, k_t + 24 of a stage
+  // a thread owns the four-column piece sc_t of rows k_t and k_t + 8 of every stage: it copies and converts them
   const int k_t = threadIdx.x >> 4, sc_t = (threadIdx.x & 15) * 4;
   const float* src_a = gram_src4(a, 0, ti * kGramTile + sc_t);
   const float* src_b = diag ? nullptr : gram_src4(a, 0, tj * kGramTile + sc_t);
@@ -300,44 +304,43 @@ __global__ void __launch_bounds__(kGramMmaThreads, 4) gram_mma_kernel(const Gram
   }
   auto issue = [&](long long r0) {
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
+    for (int h = 0; h < 2; ++h) {
       const int k = k_t + 8 * h;
       const long long row = r0 + k;
       const bool ok = row < r_end;
       gram_cp16(&Fa[k][sc_t], (ok && src_a) ? src_a + row * ld_a : nullptr);
       if (!diag) gram_cp16(&Fb[k][sc_t], (ok && src_b) ? src_b + row * ld_b : nullptr);
     }
-    if (threadIdx.x < kGramKC) {
-      const long long row = r0 + threadIdx.x;
-      gram_cp4(&Fw[threadIdx.x], (a.wgt != nullptr && row < r_end) ? a.wgt + row : nullptr);
-      gram_cp4(&Fy[threadIdx.x], (a.y != nullptr && row < r_end) ? a.y + row : nullptr);
-    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   if (r_begin < r_end) issue(r_begin);
-  for (long long r0 = r_begin; r0 < r_end; r0 += kGramKC) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                 // stage landed for everyone; everyone finished the previous products
-    // fp32 -> fp64, two columns per thread and step: a quarter warp stores 128 contiguous bytes
+  int buf = 0;
+  for (long long r0 = r_begin; r0 < r_end; r0 += kGramMK, buf ^= 1) {
+    PStage Pa = P0 + (size_t)buf * kPRows, Pb = Pa + kGramMK;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");       // this thread's own pieces have landed
+    // fp32 -> fp64 of the own pieces (the row weight rides on the left factor, product formed in fp32 as
+    // XS.T * U does in the reference)
 #pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      const int idx = threadIdx.x + kGramMmaThreads * h;
-      const int k = idx >> 5, sc = (idx & 31) * 2;
-      const float2 xa = *reinterpret_cast<const float2*>(&Fa[k][sc]);
-      const float2 xb = diag ? xa : *reinterpret_cast<const float2*>(&Fb[k][sc]);
-      // the weight rides on the left factor (product formed in fp32, as XS.T * U does in the reference)
-      if (a.wgt != nullptr) {
-        const float wv = Fw[k];
-        *reinterpret_cast<double2*>(&Pa[k][sc]) = make_double2((double)(xa.x * wv), (double)(xa.y * wv));
-      } else {
-        *reinterpret_cast<double2*>(&Pa[k][sc]) = make_double2((double)xa.x, (double)xa.y);
-      }
-      *reinterpret_cast<double2*>(&Pb[k][sc]) = make_double2((double)xb.x, (double)xb.y);
+    for (int h = 0; h < 2; ++h) {
+      const int k = k_t + 8 * h;
+      const long long row = r0 + k;
+      const float wv = (a.wgt != nullptr && row < r_end) ? __ldg(a.wgt + row) : 1.f;
+      const float4 xa = *reinterpret_cast<const float4*>(&Fa[k][sc_t]);
+      const float4 xb = diag ? xa : *reinterpret_cast<const float4*>(&Fb[k][sc_t]);
+      *reinterpret_cast<double2*>(&Pa[k][sc_t]) = make_double2((double)(xa.x * wv), (double)(xa.y * wv));
+      *reinterpret_cast<double2*>(&Pa[k][sc_t + 2]) = make_double2((double)(xa.z * wv), (double)(xa.w * wv));
+      *reinterpret_cast<double2*>(&Pb[k][sc_t]) = make_double2((double)xb.x, (double)xb.y);
+      *reinterpret_cast<double2*>(&Pb[k][sc_t + 2]) = make_double2((double)xb.z, (double)xb.w);
     }
-    if (threadIdx.x < kGramKC) Py[threadIdx.x] = Fy[threadIdx.x];
-    __syncthreads();                 // float64 stage complete, fp32 stage free again
-    if (r0 + kGramKC < r_end) issue(r0 + kGramKC);
+    if (diag && threadIdx.x < kGramMK) {
+      const long long row = r0 + threadIdx.x;
+      Py[buf * kGramMK + threadIdx.x] = (a.y != nullptr && row < r_end) ? __ldg(a.y + row) : 0.f;
+    }
+    if (r0 + kGramMK < r_end) issue(r0 + kGramMK);             // own pieces only: nobody else reads them
+    // ONE barrier per stage: this buffer is complete, and everyone has finished the products of the stage before
+    // last, which used the buffer the NEXT conversion will overwrite
+    __syncthreads();
     if (!diag) {
       const int ca = wi * 32 + fc, cb = wj * 32 + fc;
       if (ni == 4 && nj == 4) gram_stage_offdiag<4, 4>(acc, Pa, Pb, fk, ca, cb);
@@ -346,15 +349,14 @@ __global__ void __launch_bounds__(kGramMmaThreads, 4) gram_mma_kernel(const Gram
       else if (ni == 4 && nj == 3) gram_stage_offdiag<4, 3>(acc, Pa, Pb, fk, ca, cb);
       // (ni < 4 only happens in the last tile, which is never the left one of an off-diagonal pair; nj == 0: nothing)
     } else {
-      if (nd == 8) gram_stage_diag_w<8>(warp, acc, Pa, Pb, fk, fc);
-      else if (nd > 4) gram_stage_diag_w<8>(warp, acc, Pa, Pb, fk, fc);   // partial: whole tile, padding unused
+      if (nd > 4) gram_stage_diag_w<8>(warp, acc, Pa, Pb, fk, fc);   // (a partial tile runs whole: padding unused)
       else gram_stage_diag_w<4>(warp, acc, Pa, Pb, fk, fc);
       if (threadIdx.x < kGramTile) {
-#pragma unroll 8
-        for (int k = 0; k < kGramKC; ++k) {
+#pragma unroll
+        for (int k = 0; k < kGramMK; ++k) {
           const double v = Pa[k][threadIdx.x];
           cs += v;
-          cy = fma(v, (double)Py[k], cy);
+          cy = fma(v, (double)Py[buf * kGramMK + k], cy);
         }
       }
     }

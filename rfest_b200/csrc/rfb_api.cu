@@ -115,7 +115,7 @@ struct rfb_engine {
   int64_t launches = 0;
   void* comm = nullptr;
   int rank = 0, world = 1;
-  Scratch stage, zbuf, stbuf, sxybuf, small, bsplit;
+  Scratch stage, zbuf, stbuf, sxybuf, small, bsplit, gram_part;
   // host -> device staging ring of rfb_block_project: kRingSlots pinned bounce buffers + device slabs on a copy
   // stream, so the host memcpy of slab i+1, the DMA of slab i and the projection kernels of slab i-1 overlap
   static constexpr int kRingSlots = 3;
@@ -1039,7 +1039,7 @@ extern "C" int rfb_engine_destroy(rfb_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-  for (Scratch* s : {&e->stage, &e->zbuf, &e->stbuf, &e->sxybuf, &e->small, &e->bsplit}) cudaFree(s->p);
+  for (Scratch* s : {&e->stage, &e->zbuf, &e->stbuf, &e->sxybuf, &e->small, &e->bsplit, &e->gram_part}) cudaFree(s->p);
   for (int k = 0; k < rfb_engine::kRingSlots; ++k) {
     if (e->ring_pinned[k]) cudaFreeHost(e->ring_pinned[k]);
     if (e->ring_dev[k]) cudaFree(e->ring_dev[k]);
@@ -2110,14 +2110,15 @@ static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float*
     CU(cudaFuncSetAttribute(gram_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramMmaSmem));
     gram_attr = true;
   }
-  double *d_part = nullptr, *d_out = nullptr;
-  if (cudaMalloc(&d_part, sizeof(double) * n_entries * slabs) != cudaSuccess ||
-      cudaMalloc(&d_out, sizeof(double) * n_entries) != cudaSuccess) {
-    cudaFree(d_part);
+  // partial sums + result live in a scratch buffer the engine keeps (a cudaMalloc / cudaFree pair of a few hundred
+  // MB per call cost up to tens of milliseconds on some boxes)
+  if (scratch_reserve(e, e->gram_part, sizeof(double) * n_entries * ((size_t)slabs + 1)) != RFB_OK) {
     cudaGetLastError();
     return fail(RFB_ERR_CUDA, "out of device memory for the Gram partial sums (%zu bytes)",
                 sizeof(double) * n_entries * (slabs + 1));
   }
+  double* d_part = (double*)e->gram_part.p;
+  double* d_out = d_part + n_entries * (size_t)slabs;
   a.part = d_part;
   if (e->gram_mma) gram_mma_kernel<<<dim3(a.n_pairs, slabs), kGramMmaThreads, kGramMmaSmem, e->stream>>>(a);
   else gram_kernel<<<dim3(a.n_pairs, slabs), kGramThreads, kGramSmem, e->stream>>>(a);
@@ -2135,8 +2136,6 @@ static int gram_impl(rfb_model* m, int kind, int col_lo, int ncols, const float*
     if (xty) cudaMemcpyAsync(xty, d_out + cc + ncols, sizeof(double) * ncols, cudaMemcpyDeviceToHost, e->stream);
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(RFB_ERR_CUDA, "gram copy-back failed");
   }
-  cudaFree(d_part);
-  cudaFree(d_out);
   return rc;
 }
 
