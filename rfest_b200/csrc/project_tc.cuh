@@ -80,6 +80,7 @@ struct TcArgs {
   int ldz;
   int tmem_cols;      // power of two >= 2 * n_pad (two accumulators) + 128 (two A stages of hi|lo)
   int drain;          // K tiles accumulated in TMEM before the partial sums move to registers
+  int products;       // 3 (default): A_lo.B_hi + A_hi.B_lo + A_hi.B_hi; 2 / 1: measurement only (drops the first / first two)
   int n_raw;          // raw A slots
 };
 
@@ -415,9 +416,10 @@ spatial_project_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
           for (int ks = 0; ks < kTcK / 8; ++ks) {
             // 8 tf32 = 32 bytes along K inside the swizzle atom = 2 descriptor units, 8 TMEM columns
             const uint32_t ko = 2u * ks, kc = 8u * ks;
-            tc::mma_tf32_ts(elected, d, a_lo + kc, bhi + ko, idesc, (first && ks == 0) ? 0u : 1u);
-            tc::mma_tf32_ts(elected, d, a_hi + kc, blo + ko, idesc, 1);
-            tc::mma_tf32_ts(elected, d, a_hi + kc, bhi + ko, idesc, 1);
+            uint32_t accum = (first && ks == 0) ? 0u : 1u;
+            if (a.products >= 3) { tc::mma_tf32_ts(elected, d, a_lo + kc, bhi + ko, idesc, accum); accum = 1u; }
+            if (a.products >= 2) { tc::mma_tf32_ts(elected, d, a_hi + kc, blo + ko, idesc, accum); accum = 1u; }
+            tc::mma_tf32_ts(elected, d, a_hi + kc, bhi + ko, idesc, accum);
           }
           tc::commit_if(elected, bar_aempty(sa));        // stages reusable once these MMAs have read them
           tc::commit_if(elected, bar_bempty(sb));

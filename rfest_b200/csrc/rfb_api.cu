@@ -1399,6 +1399,7 @@ static bool tc_launch(rfb_engine* e, const TcPlan& tp, const float* d_stim, int6
   a.ldz = n_q;
   a.tmem_cols = tp.tmem_cols;
   a.drain = tp.drain;
+  a.products = getenv("RFB_TC_PRODUCTS") ? std::max(1, std::min(3, atoi(getenv("RFB_TC_PRODUCTS")))) : 3;
   a.n_raw = tp.n_raw;
   const int64_t tiles = (nz + kTcM - 1) / kTcM;
   const int grid = (int)std::min<int64_t>(tiles, e->num_sms);
@@ -1426,6 +1427,7 @@ static bool tc_launch_fused(rfb_engine* e, const TcPlan& tp, const float* d_stim
   a.ldz = n_q;
   a.tmem_cols = tp.tmem_cols;
   a.drain = tp.drain;
+  a.products = getenv("RFB_TC_PRODUCTS") ? std::max(1, std::min(3, atoi(getenv("RFB_TC_PRODUCTS")))) : 3;
   a.n_raw = tp.fused_n_raw;
   TcFuseArgs f{};
   f.off = off;
