@@ -92,8 +92,13 @@ int rfb_engine_launch_count(rfb_engine* e, int64_t* out);
  * "sweep_staged" (1 = rows staged through shared memory by cp.async.bulk, 0 = direct loads),
  * "sweep_stages" (ring depth per warp), "sweep_warps" (warps per CTA), "sweep_ctas" (CTAs per
  * SM, 0 = as many as fit), "sweep_sub" (subunit models on the subunit sweep: 3 = default mapping,
- * 0 = off, 1 / 2 = the mappings it was measured against).  Also read from RFB_SWEEP_* environment
- * variables at creation. */
+ * 0 = off, 1 / 2 = the mappings it was measured against, 4-7 = the pooled / tensor-memory variants).  Also read
+ * from RFB_SWEEP_* environment variables at creation.  Further keys: "project_tc" (spatial projection on
+ * tcgen05, default 1), "project_fused" (spatial + temporal projection in one kernel, default 0: measured
+ * slower), "project_slab_rows", "h2d_overlap" / "h2d_threads" (host-array ring), "fit_persistent" (small
+ * models as one persistent kernel, default 1), "gram_mma" (Gram matrices on the FP64 tensor-core
+ * instructions, default 1), "xchg" (multi-GPU exchange: 1 = fused over NVLink peer memory, 0 = NCCL,
+ * 3 = the one-CTA variant). */
 int rfb_engine_set_option(rfb_engine* e, const char* key, int value);
 /* the engine's CUDA stream (cudaStream_t as an integer), for event timing by the caller */
 int rfb_engine_stream(rfb_engine* e, uint64_t* out);
