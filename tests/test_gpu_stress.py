@@ -2,12 +2,13 @@
 
 Every hand-rolled pipeline of the engine (per-warp bulk-copy rings with mbarriers, the pooled stages with a
 producer warp, the tensor-memory accumulators, the host->device ring with events, the persistent kernel's
-grid barrier) is exercised under randomly drawn warps / CTAs / stage depths / slab sizes / thread counts.
+grid barrier, the fused projection's Z ring) is exercised under randomly drawn warps / CTAs / stage depths / slab sizes / thread counts.
 A synchronisation bug shows up as a result that depends on the geometry; here every geometry must
 reproduce the default geometry's loss, gradient, predictions and short fit to fp32 summation noise, and
 itself bit for bit when repeated.
 """
 
+import os
 import zlib
 
 import numpy as np
@@ -18,7 +19,8 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 DEFAULTS = dict(sweep_warps=4, sweep_ctas=-1, sweep_stages=0, sweep_staged=1, sweep_sub=3, sweep_pool_ctas=0,
-                project_slab_rows=0, h2d_threads=8, h2d_overlap=1, fit_persistent=1, fit_small_ctas=0)
+                project_slab_rows=0, h2d_threads=8, h2d_overlap=1, fit_persistent=1, fit_small_ctas=0,
+                project_fused=0)
 
 
 def _draw(rng):
@@ -27,7 +29,7 @@ def _draw(rng):
                 sweep_sub=int(rng.choice([0, 3, 4, 5, 6, 7])), sweep_pool_ctas=int(rng.choice([0, 1, 2, 5])),
                 project_slab_rows=int(rng.choice([0, 4096, 4100, 9973])), h2d_threads=int(rng.integers(1, 9)),
                 h2d_overlap=int(rng.choice([0, 1, 1])), fit_persistent=int(rng.choice([0, 1, 2, 3])),
-                fit_small_ctas=int(rng.choice([0, 1, 3, 17, 148])))
+                fit_small_ctas=int(rng.choice([0, 1, 3, 17, 148])), project_fused=int(rng.choice([0, 1])))
 
 
 def _apply(opts):
@@ -80,7 +82,7 @@ def test_results_do_not_depend_on_launch_geometry(model):
     rng = np.random.default_rng(zlib.crc32(model.encode()))
     try:
         base = _run(model, DEFAULTS)
-        for trial in range(6):
+        for trial in range(int(os.environ.get("RFB_STRESS_TRIALS", "6"))):      # (soak runs: more draws)
             opts = _draw(rng)
             got = _run(model, opts)
             again = _run(model, opts) if trial < 2 else None
