@@ -21,7 +21,8 @@ import helpers
 # "g3d" = helpers.data_3d_stim (the reference's tests/test_glm.py fixture, seeded).
 _BASE = dict(data="lnp", n=2603, dims=(8, 5, 4), df=(4, 3, 3), seed=31, n_train=2000,
              hist=(6, 4), init="random", p0_scale=0.1, icpt=0.02, iters=60, tolerance=0,
-             min_iters=300, return_model=None, compute_ci=False, test=False, verbose=0)
+             min_iters=300, return_model=None, compute_ci=False, test=False, verbose=0, smooth="cr",
+             hist_smooth="cr")
 
 
 def _case(**kw):
@@ -100,6 +101,14 @@ CASES = {
                                      iters=40),
     "softmax_output": _case(distr="poisson", out_nl="softmax", filt_nl="none", subunits=1,
                             alpha=1.0, beta=0.01, step=0.02, metric="corrcoef", history=True, dev=True, iters=40),
+    # the other spline bases (rfest/splines.py:6-36,97-189): B-splines, cyclic cubic and thin-plate regression splines
+    "lnp_bspline_dev": _case(distr="poisson", out_nl="softplus", filt_nl="none", subunits=1, smooth="bs",
+                             hist_smooth="bs", alpha=1.0, beta=0.01, step=0.05, metric="corrcoef", history=True,
+                             dev=True, iters=40),
+    "lg_thin_plate_2sub": _case(distr="gaussian", out_nl="none", filt_nl="tanh", subunits=2, smooth="tp",
+                                alpha=0.5, beta=0.001, step=0.03, metric="mse", history=True, dev=True, iters=40),
+    "lnp_cyclic": _case(distr="poisson", out_nl="exponential", filt_nl="none", subunits=1, smooth="cc",
+                        alpha=1.0, beta=0.01, step=0.01, metric="r2", history=False, dev=False, iters=40),
     "softmax_both_gaussian": _case(distr="gaussian", out_nl="softmax", filt_nl="softmax", subunits=1,
                                    alpha=1.0, beta=0.0, step=0.005, metric="mse", history=True, dev=False,
                                    iters=40),
@@ -155,12 +164,12 @@ def run_case(make, name, dtype, reference_quirks=False, data=None):
     hshift = 1 if c["data"] == "lnp" else 0
     m = make(c["distr"], c["out_nl"])
     tr, dv = data["train"], data["dev"]
-    m.add_design_matrix(tr[0], dims=dims, df=df, smooth="cr", filter_nonlinearity=c["filt_nl"],
+    m.add_design_matrix(tr[0], dims=dims, df=df, smooth=c["smooth"], filter_nonlinearity=c["filt_nl"],
                         kind="train", name="stimulus")
     if dv is not None:
         m.add_design_matrix(dv[0], dims=dims, df=df, name="stimulus", kind="dev")
     if c["history"]:
-        m.add_design_matrix(tr[1], dims=[hl], df=[hdf], smooth="cr", shift=hshift, kind="train",
+        m.add_design_matrix(tr[1], dims=[hl], df=[hdf], smooth=c["hist_smooth"], shift=hshift, kind="train",
                             filter_nonlinearity="none", name="history")
         if dv is not None:
             m.add_design_matrix(dv[1], dims=[hl], df=[hdf], kind="dev", name="history")
